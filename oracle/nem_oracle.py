@@ -1,0 +1,360 @@
+"""CPU oracle for the NEM-scoring-inside-order-MCMC hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this
+module; it is used by ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` as the checker /
+the CPU arm, never as the thing that is shipped.
+
+This is a numpy restatement of the reference's algorithm (pure Python/numpy
+reference at MrGreyPanda/NEM-MCMC-optimization).  Every function cites the
+reference ``file:line`` it follows.  Parity status:
+
+* score path      - PINNED: 20 ``obs_ll`` + 1 ``real_ll`` golden values logged by
+                    the reference (tests/golden/networks.json) reproduce here.
+* closure         - PINNED: 20 ``networkN_red.csv -> networkN.csv`` pairs and
+                    reference ``utils.ancestor`` outputs in tests/golden.
+* data synthesis  - PINNED: known-answer test of the reference
+                    (tests/utils.tests.py:11-27) + the goldens above.
+* MCMC trajectory - parity UNPINNED in the reference (no assertion anywhere,
+                    driver raises NameError at HEAD); the loop below restates
+                    nem_order_mcmc.py:272-302 with a counter-based Philox RNG
+                    so the GPU path can be compared draw for draw.
+"""
+from __future__ import annotations
+
+import random as _pyrandom
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# data synthesis (utils.py:5-35)
+# --------------------------------------------------------------------------
+
+
+def create_connection_mat(s_mat):
+    """utils.py:5-13 - reflexive transpose of the adjacency."""
+    s_mat = np.asarray(s_mat)
+    dim_s = s_mat.shape[1]
+    conn = np.zeros((dim_s, dim_s))
+    conn[np.arange(dim_s), np.arange(dim_s)] = 1
+    conn[(s_mat.T == 1)] = 1
+    return conn
+
+
+def create_real_knockdown_mat(s_mat, e_arr):
+    """utils.py:15-23 - E-gene k attached to S-gene e_arr[k] reacts to the
+    knock-down of e_arr[k] and of every i with adj[i][e_arr[k]] == 1."""
+    conn = create_connection_mat(s_mat)
+    e_arr = np.asarray(e_arr, dtype=np.int64)
+    # knockdown[i][k] = conn[e_arr[k]][i]
+    return conn[e_arr, :].T.copy()
+
+
+def create_observed_knockdown_mat(knockdown_mat, alpha, beta, seed=42):
+    """utils.py:25-35 - one ``random.random()`` per cell in row-major order
+    (MT19937, seed 42 by default - see SURVEY Q9), FP flip < alpha, FN flip < beta."""
+    rng = _pyrandom.Random(seed)
+    kd = np.asarray(knockdown_mat)
+    s, e = kd.shape
+    u = np.array([rng.random() for _ in range(s * e)]).reshape(s, e)
+    out = kd.copy()
+    out[(kd == 0) & (u < alpha)] = 1
+    out[(kd == 1) & (u < beta)] = 0
+    return out
+
+
+def initial_order_guess(observed_knockdown_mat):
+    """utils.py:56-64 - argsort of minus the row sums."""
+    return np.argsort(-np.sum(observed_knockdown_mat, axis=1))
+
+
+def nem_constants(alpha, beta):
+    """nem.py:17-18."""
+    return float(np.log(alpha / (1.0 - beta))), float(np.log(beta / (1.0 - alpha)))
+
+
+# --------------------------------------------------------------------------
+# score tables (nem.py:25-64)
+# --------------------------------------------------------------------------
+
+
+def score_tables(D, A, B):
+    """T, N, U of SURVEY section 8.
+
+    T[j] = where(D[j]==0, B, -A)          nem.py:46
+    N    = sum_k where(D[k]==0, 0, A)     nem.py:62
+    U[i] = base row of table i            nem.py:27-32,59-62  (== T[i] + N up to rounding)
+    U is built with the reference's own summation order so that it is bit-identical.
+    """
+    D = np.asarray(D)
+    s, e = D.shape
+    T = np.where(D == 0, B, -A).astype(np.float64)
+    U = np.empty((s + 1, e))
+    for node in range(s):
+        score = np.where(D[node, :] == 1, 0, B).astype(np.float64)  # nem.py:27
+        for index in range(s):  # nem.py:30-32 (set iteration order of small ints is ascending)
+            if index != node:
+                score = score + np.where(D[index, :] == 1, A, 0)
+        U[node] = score
+    U[s] = np.where(D == 0, 0, A).sum(axis=0)  # nem.py:62
+    return T, U[s].copy(), U
+
+
+# --------------------------------------------------------------------------
+# closure (utils.py:37-54)
+# --------------------------------------------------------------------------
+
+
+def closure_pathcount(adj):
+    """utils.py:37-54 restated on float input (the int64 call wraps for
+    dense S>=66): sum_{k=1..S} M^k > 0."""
+    m = np.asarray(adj, dtype=np.float64)
+    s = m.shape[0]
+    p = m.copy()
+    acc = m.copy()
+    for _ in range(1, s):
+        p = p.dot(m)
+        acc += p
+    return (acc > 0).astype(np.int64)
+
+
+def closure_bool(adj):
+    """Mathematical transitive closure (boolean Warshall).  Equals utils.ancestor
+    whenever path counts < 2**63 (always for S <= 64)."""
+    r = np.asarray(adj).astype(bool).copy()
+    s = r.shape[0]
+    for k in range(s):
+        r |= np.outer(r[:, k], r[k, :])
+    return r.astype(np.int64)
+
+
+def transitive_reduction(adj):
+    """utils.py:120-129."""
+    a = np.array(adj, copy=True)
+    n = a.shape[0]
+    for k in range(n):
+        for i in range(n):
+            if a[i][k]:
+                for j in range(n):
+                    if i != j and a[k][j]:
+                        a[i][j] = 0
+    return a
+
+
+# --------------------------------------------------------------------------
+# score (nem.py:72-86, 132-142; utils.py:66-94)
+# --------------------------------------------------------------------------
+
+
+def score_loops(adj, D, A, B, U=None, T=None):
+    """Faithful restatement of nem.py:132-142 (same loops, same op order):
+
+    parents_list[j] = [i for i if adj[i][j]==1], weights 1.0        nem.py:132-140
+    cell[j] += log(1 - w + w*exp(T[i])) for each parent            nem.py:72-80
+    ll = sum(logaddexp.reduce(cell, axis=0))                       nem.py:82-86
+    """
+    adj = np.asarray(adj)
+    s = adj.shape[0]
+    if U is None or T is None:
+        T, _, U = score_tables(D, A, B)
+    cell = U.copy()
+    w = 1.0
+    for j in range(s):
+        for i in range(s):
+            if adj[i][j] == 1 and i != j:
+                cell[j, :] += np.log(1.0 - w + w * np.exp(T[i]))
+    cell_sums = np.logaddexp.reduce(cell, axis=0)
+    return sum(cell_sums)
+
+
+def score_matrix(adj, D, A, B):
+    """Matrix form of the same score:
+    ll = sum_e N[e] + sum_e LSE(0, (Phi'^T T)[:, e]),  Phi' = I | adj."""
+    adj = np.asarray(adj)
+    s = adj.shape[0]
+    D = np.asarray(D, dtype=np.float64)
+    T = np.where(D == 0, B, -A)
+    N = (A * D).sum(axis=0)
+    phi = (adj != 0).astype(np.float64)
+    phi[np.arange(s), np.arange(s)] = 1.0
+    v = phi.T @ T  # (S, E)
+    m = np.maximum(v.max(axis=0), 0.0)
+    lse = m + np.log(np.exp(-m) + np.exp(v - m).sum(axis=0))
+    return float(N.sum() + lse.sum())
+
+
+def score_counts(adj, D, A, B):
+    """Integer-count form used by the CUDA path: v[j,e] = B*c_j - (A+B)*n[j,e]
+    with n = Phi'^T D (exact integers) and c_j = |ancestors(j)|+1."""
+    adj = np.asarray(adj)
+    s = adj.shape[0]
+    Di = np.asarray(D).astype(np.int64)
+    phi = (adj != 0).astype(np.int64)
+    phi[np.arange(s), np.arange(s)] = 1
+    n = phi.T @ Di
+    c = phi.sum(axis=0)
+    v = B * c[:, None] - (A + B) * n
+    m = np.maximum(v.max(axis=0), 0.0)
+    lse = m + np.log(np.exp(-m) + np.exp(v - m).sum(axis=0))
+    return float(A * Di.sum() + lse.sum())
+
+
+# --------------------------------------------------------------------------
+# order -> graph (nem_order_mcmc.py:54-77, 210-221)
+# --------------------------------------------------------------------------
+
+RULE_FULL = 0    # W = permissibility mask (every earlier node is a parent)
+RULE_MASKED = 1  # W = permissibility & candidate-edge mask
+
+
+def permissible(order):
+    """nem_order_mcmc.py:63-64: parents(i) = perm_order[:pos(i)].
+    Returns P with P[a][b] = 1 iff a is placed before b (edge a->b permissible)."""
+    order = np.asarray(order)
+    s = len(order)
+    pos = np.empty(s, dtype=np.int64)
+    pos[order] = np.arange(s)
+    return (pos[:, None] < pos[None, :]).astype(np.int64)
+
+
+def order_to_graph(order, rule=RULE_FULL, cand=None, use_nem=True):
+    """The DAG the chain scores for an order.  adjacency convention adj[a][b]=1
+    iff edge a->b (== reference ``dag = W.T``, nem_order_mcmc.py:213).
+    use_nem=True closes it (create_nem, :216-221); False leaves it (create_dag, :210-214)."""
+    g = permissible(order)
+    if rule == RULE_MASKED:
+        g = g & (np.asarray(cand) != 0)
+    if use_nem:
+        g = closure_bool(g)
+    return g
+
+
+# --------------------------------------------------------------------------
+# Philox4x32-10 (Salmon et al. 2011), counter-based RNG shared with the CUDA path
+# --------------------------------------------------------------------------
+
+_PH_M0, _PH_M1 = 0xD2511F53, 0xCD9E8D57
+_PH_W0, _PH_W1 = 0x9E3779B9, 0xBB67AE85
+_M32 = 0xFFFFFFFF
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    for _ in range(10):
+        p0 = _PH_M0 * c0
+        p1 = _PH_M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & _M32, p1 & _M32, ((p0 >> 32) ^ c3 ^ k1) & _M32, p0 & _M32
+        k0 = (k0 + _PH_W0) & _M32
+        k1 = (k1 + _PH_W1) & _M32
+    return c0, c1, c2, c3
+
+
+def propose(order, r, swap_prob_u32):
+    """nem_order_mcmc.py:231-255 (positions are swapped, Q5): with prob swap_prob swap two
+    distinct uniformly chosen positions (random.sample(range(S),2)), else positions i,i+1
+    with i ~ U{0..S-2}.  r = 4 Philox words; integer ranges by mulhi."""
+    s = len(order)
+    new = np.array(order, copy=True)
+    if r[0] < swap_prob_u32:
+        i = (r[1] * s) >> 32
+        j = (r[2] * (s - 1)) >> 32
+        if j >= i:
+            j += 1
+    else:
+        i = (r[1] * (s - 1)) >> 32
+        j = i + 1
+    new[i], new[j] = new[j], new[i]
+    return new
+
+
+def swap_prob_to_u32(p):
+    return int(min(max(float(p), 0.0), 1.0) * 4294967296.0 + 0.5) if p < 1.0 else 0x100000000
+
+
+def mcmc_chain(D, A, B, order0, n_iter, gamma, swap_prob=0.95, seed=1234, chain=0,
+               rule=RULE_FULL, cand=None, use_nem=True, score_fn=None, burn_in=0):
+    """Restatement of NEMOrderMCMC.method's loop, nem_order_mcmc.py:272-302, with the clean
+    (no-expit) score nem.py:72-86 and a deterministic order->DAG rule.
+
+    Per iteration t the RNG draw is philox(counter=(t_lo, t_hi, chain, 0), key=(seed_lo, seed_hi)):
+      r0 -> swap-vs-adjacent, r1/r2 -> positions, r3 -> accept uniform u=(r3+0.5)/2**32.
+    accept iff u < exp(gamma*(score-curr))                           (:224-229)
+    Returns dict with best/current state, accept count, per-iteration score lists and
+    edge counts (sum over post-burn-in iterations of the current graph - new, not in reference)."""
+    if score_fn is None:
+        score_fn = lambda g: score_counts(g, D, A, B)
+    s = D.shape[0]
+    sp = swap_prob_to_u32(swap_prob)
+    k0, k1 = seed & _M32, (seed >> 32) & _M32
+    curr_order = np.array(order0, dtype=np.int64)
+    curr_g = order_to_graph(curr_order, rule, cand, use_nem)
+    curr = score_fn(curr_g)
+    best, best_order, best_g = curr, curr_order.copy(), curr_g.copy()
+    all_scores, curr_scores = [curr], [curr]
+    n_acc = 0
+    edge_counts = np.zeros((s, s), dtype=np.int64)
+    for t in range(n_iter):
+        r = philox4x32_10(t & _M32, (t >> 32) & _M32, chain & _M32, 0, k0, k1)
+        cand_order = propose(curr_order, r, sp)
+        g = order_to_graph(cand_order, rule, cand, use_nem)
+        ll = score_fn(g)
+        all_scores.append(ll)
+        curr_scores.append(curr)
+        u = (r[3] + 0.5) / 4294967296.0
+        with np.errstate(over="ignore"):
+            rate = np.exp(gamma * (ll - curr))
+        if u < rate:
+            n_acc += 1
+            curr, curr_order, curr_g = ll, cand_order, g
+            if curr > best:
+                best, best_order, best_g = curr, curr_order.copy(), curr_g.copy()
+        if t >= burn_in:
+            edge_counts += curr_g
+    return dict(best_score=best, best_order=best_order, best_graph=best_g, curr_score=curr,
+                curr_order=curr_order, n_accept=n_acc, all_score_list=all_scores,
+                curr_score_list=curr_scores, edge_counts=edge_counts)
+
+
+# --------------------------------------------------------------------------
+# synthetic inputs (DAGs/rnd_dag_gen.py:47-103 edge law)
+# --------------------------------------------------------------------------
+
+
+def rank_layout(S):
+    """(nodes per rank, ranks) with p*r == S as in SURVEY 8d."""
+    table = {10: (2, 5), 20: (4, 5), 30: (5, 6), 50: (5, 10), 100: (10, 10)}
+    if S in table:
+        return table[S]
+    for p in range(int(S ** 0.5), 0, -1):
+        if S % p == 0:
+            return p, S // p
+    return 1, S
+
+
+def gen_rnd_dag(S, rng, percent=40):
+    """Edge law of rnd_dag_gen.py:63-79: ranks of p nodes, nodes numbered in topological
+    order, each (older node, new node) pair kept iff randint(0,100) < percent (40/101).
+    Returns the *unclosed* adjacency (adj[a][b]=1 iff edge a->b)."""
+    p, r = rank_layout(S)
+    adj = np.zeros((S, S), dtype=np.int64)
+    nodes = 0
+    for _ in range(r):
+        if nodes:
+            keep = rng.integers(0, 101, size=(nodes, p)) < percent
+            adj[:nodes, nodes:nodes + p] = keep
+        nodes += p
+    return adj
+
+
+def synth_dataset(S, E, seed=0, alpha=0.05, beta=0.1):
+    """true DAG by the rnd_dag_gen edge law (closed), end_nodes ~ U{0..S-1} i.i.d.
+    (rnd_dag_gen.py:89-90), D = observed(real) with the per-cell flip rule utils.py:25-35
+    (vectorised default_rng for large E)."""
+    rng = np.random.default_rng(seed)
+    adj = closure_bool(gen_rnd_dag(S, rng))
+    end_nodes = rng.integers(0, S, size=E)
+    real = create_real_knockdown_mat(adj, end_nodes)
+    u = rng.random(real.shape)
+    D = real.copy()
+    D[(real == 0) & (u < alpha)] = 1
+    D[(real == 1) & (u < beta)] = 0
+    return adj, end_nodes, D.astype(np.uint8)

@@ -1,0 +1,22 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """Fixtures produced by running the reference (tests/golden/make_golden.py)."""
+    arr = np.load(os.path.join(ROOT, "tests", "golden", "networks.npz"))
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "networks.json")))
+    return arr, meta

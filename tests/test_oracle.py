@@ -1,0 +1,143 @@
+"""The oracle is pinned against the reference's golden vectors (CPU only)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, nem_oracle as orc
+
+NETS = list(range(20))
+
+
+@pytest.mark.parametrize("n", NETS)
+def test_obs_ll_golden_exact(golden, n):
+    """20 obs_ll values the reference logged/reproduced: faithful-loop oracle is bit-exact,
+    matrix/count/C forms agree to 1e-10 relative."""
+    arr, meta = golden
+    info = meta["networks"][str(n)]
+    adj, D = arr[f"adj{n}"].astype(np.int64), arr[f"D{n}"]
+    A, B = info["A"], info["B"]
+    assert info["obs_ll"] == meta["logged_obs_ll"][str(n)]
+    assert orc.nem_constants(info["alpha"], info["beta"]) == (A, B)
+    T, N, U = orc.score_tables(D, A, B)
+    assert np.array_equal(U, arr[f"U{n}"])  # nem.py:56-64 bit-exact
+    np.fill_diagonal(adj, 0)
+    assert orc.score_loops(adj, D, A, B, U, T) == info["obs_ll"]
+    for f in (orc.score_matrix, orc.score_counts, c_oracle.score):
+        assert f(adj, D, A, B) == pytest.approx(info["obs_ll"], rel=1e-10, abs=1e-9)
+
+
+def test_real_ll_network11(golden):
+    """net11/result.txt:9 'Real Score: 14.426982994013326'.  compute_real_score(real matrix) builds
+    the tables from the noise-free matrix but the null row of U from the OBSERVED one
+    (nem.py:62 reads self.observed_knockdown_mat) - restate exactly that."""
+    arr, meta = golden
+    info = meta["networks"]["11"]
+    assert info["real_ll"] == 14.426982994013326
+    adj = arr["adj11"].astype(np.int64)
+    np.fill_diagonal(adj, 0)
+    A, B = info["A"], info["B"]
+    T, _, U = orc.score_tables(arr["real11"], A, B)
+    U[-1] = np.where(arr["D11"] == 0, 0, A).sum(axis=0)
+    assert orc.score_loops(adj, arr["real11"], A, B, U, T) == info["real_ll"]
+
+
+@pytest.mark.parametrize("n", [0, 5, 11, 12, 19])
+def test_random_graph_scores(golden, n):
+    arr, meta = golden
+    info = meta["networks"][str(n)]
+    D, A, B = arr[f"D{n}"], info["A"], info["B"]
+    for g, ref in zip(arr[f"rg{n}"], info["rg_scores"]):
+        assert orc.score_matrix(g, D, A, B) == pytest.approx(ref, rel=1e-11)
+        assert orc.score_counts(g, D, A, B) == pytest.approx(ref, rel=1e-11)
+        assert c_oracle.score(g, D, A, B) == pytest.approx(ref, rel=1e-11)
+    got = c_oracle.score_batch(arr[f"rg{n}"], D, A, B, nthreads=3)
+    assert np.allclose(got, info["rg_scores"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("n", NETS)
+def test_closure_golden(golden, n):
+    """closure(networkN_red) == networkN (closed) == reference utils.ancestor(red)."""
+    arr, _ = golden
+    red, adj, anc = arr[f"red{n}"], arr[f"adj{n}"], arr[f"anc_red{n}"]
+    for f in (orc.closure_bool, orc.closure_pathcount, c_oracle.closure):
+        got = np.asarray(f(red))
+        assert np.array_equal(got, anc)
+        assert np.array_equal(got, adj)
+        assert np.array_equal(np.asarray(f(adj)), adj)  # idempotent
+
+
+def test_closure_dense_70(golden):
+    arr, _ = golden
+    tri = np.triu(np.ones((70, 70), dtype=np.uint8), 1)
+    assert np.array_equal(orc.closure_bool(tri), arr["anc_tri70"])
+    assert np.array_equal(c_oracle.closure(tri), arr["anc_tri70"])
+
+
+def test_knockdown_kat(golden):
+    """tests/utils.tests.py:11-27 of the reference."""
+    arr, _ = golden
+    expected = np.array([[1, 1, 1, 0, 1, 0, 1], [0, 1, 1, 0, 1, 0, 0], [0, 0, 1, 0, 1, 0, 0],
+                         [0, 0, 1, 1, 1, 0, 0], [0, 0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 1, 1, 0]])
+    assert np.array_equal(arr["kat_kd"], expected)
+    assert np.array_equal(orc.create_real_knockdown_mat(arr["kat_smat"], arr["kat_earr"]), expected)
+
+
+@pytest.mark.parametrize("n", NETS)
+def test_data_synthesis_golden(golden, n):
+    arr, meta = golden
+    info = meta["networks"][str(n)]
+    real = orc.create_real_knockdown_mat(arr[f"adj{n}"], arr[f"end{n}"])
+    assert np.array_equal(real, arr[f"real{n}"])
+    obs = orc.create_observed_knockdown_mat(real, info["alpha"], info["beta"])
+    assert np.array_equal(obs, arr[f"D{n}"])
+    assert np.array_equal(orc.initial_order_guess(obs), arr[f"order0_{n}"])
+
+
+def test_philox_known_answer():
+    """Random123 known-answer vectors for philox4x32-10."""
+    assert orc.philox4x32_10(0, 0, 0, 0, 0, 0) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    f = 0xFFFFFFFF
+    assert orc.philox4x32_10(f, f, f, f, f, f) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert orc.philox4x32_10(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0) == (
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+
+
+def test_mcmc_c_equals_numpy(golden):
+    arr, meta = golden
+    info = meta["networks"]["12"]
+    D, A, B = arr["D12"], info["A"], info["B"]
+    S, E = D.shape
+    rng = np.random.default_rng(3)
+    cand = (rng.random((S, S)) < 0.4).astype(np.uint8)
+    for rule, use_nem in ((0, True), (1, True), (1, False)):
+        kw = dict(n_iter=300, gamma=2.0 * S / E, swap_prob=0.9, seed=77, chain=5, rule=rule, cand=cand,
+                  use_nem=use_nem, burn_in=20)
+        a = orc.mcmc_chain(D, A, B, arr["order0_12"], **kw)
+        b = c_oracle.mcmc_chain(D, A, B, arr["order0_12"], keep_scores=True, **kw)
+        assert a["n_accept"] == b["n_accept"] and 0 < a["n_accept"] < 300
+        assert np.array_equal(a["best_order"], b["best_order"])
+        assert np.array_equal(a["curr_order"], b["curr_order"])
+        assert np.array_equal(a["edge_counts"], b["edge_counts"])
+        assert np.array_equal(a["best_graph"], b["best_graph"])
+        assert np.allclose(a["all_score_list"], b["all_score_list"], rtol=1e-12)
+        assert a["best_score"] == pytest.approx(b["best_score"], rel=1e-12)
+
+
+def test_mcmc_boltzmann_small():
+    """S=4: visit frequencies of orders follow exp(gamma*score) (symmetric proposal, :224-255)."""
+    import itertools
+    adj, _, D = orc.synth_dataset(4, 24, seed=1)
+    A, B = orc.nem_constants(0.05, 0.1)
+    gamma = 0.35
+    orders = list(itertools.permutations(range(4)))
+    sc = np.array([orc.score_counts(orc.order_to_graph(np.array(o)), D, A, B) for o in orders])
+    p = np.exp(gamma * (sc - sc.max())); p /= p.sum()
+    # run the C chain in segments to record visited orders
+    counts = dict.fromkeys(orders, 0)
+    order = np.arange(4, dtype=np.int32)
+    n_seg, seg = 4000, 5
+    for k in range(n_seg):
+        r = c_oracle.mcmc_chain(D, A, B, order, seg, gamma, swap_prob=0.5, seed=1000 + k, chain=0)
+        order = r["curr_order"]
+        counts[tuple(int(x) for x in order)] += 1
+    freq = np.array([counts[o] for o in orders]) / n_seg
+    assert np.abs(freq - p).max() < 0.03
