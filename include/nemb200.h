@@ -1,0 +1,147 @@
+/* nemb200.h - C ABI of the B200-native NEM scoring / order-MCMC hot path.
+ *
+ * The reference (MrGreyPanda/NEM-MCMC-optimization) is pure Python and has no FFI of its own;
+ * each entry point below names the reference method(s) (file:line under /root/reference) whose
+ * work it replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer named d_* is DEVICE memory owned by the caller (torch); the library never
+ *    allocates device memory, never synchronises the device and launches only on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  - every function returns 0 on success, <0 on error; nemb200_last_error() gives the
+ *    thread-local message of the last failure;
+ *  - graphs are bit-packed: W = (S+31)/32 uint32 words per row, rows[g][a][w] bit b set iff
+ *    edge a -> (32*w+b).  This is the reference's `dag`/`nem` orientation
+ *    (dag[a][b]==1 iff a->b, nem_order_mcmc.py:213,220); the score ignores the diagonal (it uses I|Phi),
+ *    the closure treats it like any other entry;
+ *  - orders are int32[S] position -> S-gene label (the reference's perm_order, :29-48);
+ *  - S <= 128 (tensor-core path), E arbitrary.
+ */
+#ifndef NEMB200_H
+#define NEMB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEMB200_VERSION 1
+#define NEMB200_MAX_S 128
+
+enum { NEMB200_RULE_FULL = 0, NEMB200_RULE_MASKED = 1 };
+/* score implementations (nemb200_score_batch `impl`) */
+enum {
+  NEMB200_SCORE_AUTO = 0,    /* tensor-core path, best epilogue for the dataset */
+  NEMB200_SCORE_WITNESS = 1, /* popcount + fp64 logsumexp CUDA kernel (independent witness) */
+  NEMB200_SCORE_TC_LUT = 2,  /* tcgen05 GEMM + shared-memory exp-table epilogue */
+  NEMB200_SCORE_TC_EX2 = 3,  /* tcgen05 GEMM + ex2 epilogue, fixed scale */
+  NEMB200_SCORE_TC_EX2_2PASS = 4 /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
+};
+
+typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */
+
+int nemb200_version(void);
+const char *nemb200_last_error(void);
+
+/* ---- resident data: replaces NEM.get_score_tables / build_score_table / get_node_lr_table
+ *      (nem.py:25-64) and the copies NEMOrderMCMC.__init__ keeps (nem_order_mcmc.py:40-44).
+ *      d_D: S x E row-major uint8 0/1 = NEM.observed_knockdown_mat (nem.py:19).
+ *      A, B: nem.py:17-18.  d_workspace: nemb200_dataset_bytes(S,E) bytes, 1024-byte aligned,
+ *      must outlive the handle. */
+size_t nemb200_dataset_bytes(int S, int E);
+int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A, double B,
+                           void *d_workspace, size_t workspace_bytes, void *stream,
+                           nemb200_dataset **out);
+int nemb200_dataset_destroy(nemb200_dataset *h);
+/* host-side facts about the dataset: fills info[0..7] =
+ * {S, E, W, K_pad, graphs_per_tile, lut_valid, scale_log2, n_mtiles} */
+int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int n);
+
+/* ---- transitive closure: replaces utils.ancestor (utils.py:37-54) as called by
+ *      NEMOrderMCMC.create_nem (nem_order_mcmc.py:216-221).  Boolean (mathematical) closure of the
+ *      relation as given (a DAG without self loops stays irreflexive; nodes on a cycle get their
+ *      diagonal bit, like the reference's path counts).  In-place allowed (d_out == d_adj). */
+int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_t *d_out_bits,
+                        void *stream);
+
+/* ---- batched NEM score: replaces compute_ll_ratios + calculate_ll for binary graphs
+ *      (nem.py:72-86 driven as nem.py:132-142; utils.py:66-94; nem_order_mcmc.py:79-93 without
+ *      the expit quirk).  d_phi_bits: n_graphs closed (or not) graphs; score is
+ *      sum_e N[e] + sum_e LSE(0, ((I|Phi)^T T)[:,e]).  d_scores: n_graphs float64.
+ *      d_workspace: nemb200_score_workspace_bytes(h, n_graphs) bytes. */
+size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs);
+int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_phi_bits, int n_graphs,
+                        double *d_scores, void *d_workspace, size_t workspace_bytes, int impl,
+                        void *stream);
+
+/* ---- general-weight cell ratios: replaces compute_ll_ratios / compute_cell_ratios for real-valued
+ *      parent weights (nem.py:72-80, utils.py:66-82, nem_order_mcmc.py:79-87).  d_weights: S x S
+ *      float64, w[i][j] = weight of parent j for node i (0 = no edge, diagonal ignored);
+ *      apply_expit != 0 reproduces the MCMC driver's expit-on-weights (nem_order_mcmc.py:83-86).
+ *      d_cell: (S+1) x E float64 out, row S = the null row N (nem.py:62). */
+int nemb200_cell_ratios(const nemb200_dataset *h, const double *d_weights, int apply_expit,
+                        double *d_cell, void *stream);
+
+/* ---- column logsumexp + total: replaces calculate_ll / compute_ll (nem.py:82-86,
+ *      nem_order_mcmc.py:89-93, utils.py:84-94).  d_cell: rows x E float64; d_order_weights
+ *      (rows x E, may be NULL) receives exp(cell - colsum); d_ll[0] the log-likelihood. */
+size_t nemb200_cell_ll_workspace_bytes(int E);
+int nemb200_cell_ll(const double *d_cell, int rows, int E, double *d_order_weights, double *d_ll,
+                    void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---- order -> graph: replaces get_permissible_parents (nem_order_mcmc.py:54-77) +
+ *      create_dag / create_nem (:210-221) with the deterministic rules of DESIGN.md
+ *      (FULL: every earlier node is a parent; MASKED: & d_cand_bits, S x W words shared by all
+ *      chains).  use_nem != 0 closes the graph. */
+int nemb200_order_to_graph(const int32_t *d_orders, int n_chains, int S, int rule,
+                           const uint32_t *d_cand_bits, int use_nem, uint32_t *d_out_bits,
+                           void *stream);
+
+/* ---- device-resident order-MCMC: replaces the loop of NEMOrderMCMC.method
+ *      (nem_order_mcmc.py:272-302): get_new_order (:231-255), order->graph, score, accepting
+ *      (:224-229), best-so-far bookkeeping (:290-309).  Philox4x32-10 keyed by `seed`, counter
+ *      (iteration, global chain id = chain_offset + local index, 0).
+ *      State (all device, caller-owned, n_chains leading dimension):
+ *        d_orders      int32 [n][S]      in: start orders, out: current orders
+ *        d_curr_scores f64   [n]         in (if resume) / out
+ *        d_curr_bits   u32   [n][S][W]   in (if resume) / out: current graphs
+ *        d_best_scores f64   [n], d_best_orders int32 [n][S], d_best_bits u32 [n][S][W]
+ *        d_accept      i64   [n]         accepted proposals (accumulated)
+ *        d_edge_counts u32   [n][S*S]    per-chain sum over post-burn-in iterations of the current
+ *                                        graph (may be NULL); edge a->b at [a*S+b]
+ *        d_score_trace f64   [n_iters][2][n] per iteration: proposed score, current score after the
+ *                                        accept decision (may be NULL)
+ *        d_gamma       f64   [n]         per-chain inverse temperature (gamma of :224-229)
+ *      iter0: global index of the first iteration (RNG counter / burn-in bookkeeping);
+ *      resume == 0 scores the start orders first (method(), :258).
+ *      d_workspace: nemb200_mcmc_workspace_bytes(h, n_chains) bytes. */
+size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_chains);
+int nemb200_mcmc_run(const nemb200_dataset *h, int n_chains, int64_t n_iters, int64_t iter0,
+                     int64_t burn_in, const double *d_gamma, double swap_prob, uint64_t seed,
+                     uint32_t chain_offset, int rule, const uint32_t *d_cand_bits, int use_nem,
+                     int resume, int score_impl, int32_t *d_orders, double *d_curr_scores,
+                     uint32_t *d_curr_bits, double *d_best_scores, int32_t *d_best_orders,
+                     uint32_t *d_best_bits, int64_t *d_accept, uint32_t *d_edge_counts,
+                     double *d_score_trace, void *d_workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ---- replica exchange between neighbouring chains of one ladder: replaces the swap half of
+ *      replica_exchange_step (nem_order_mcmc.py:326-340).  Chains are grouped in ladders of
+ *      `ladder` consecutive chains; phase 0 pairs (0,1),(2,3).., phase 1 pairs (1,2),(3,4)..;
+ *      swap iff u < exp(-delta), delta as :333.  States (order, graph, score) are exchanged,
+ *      gammas stay.  Philox counter (round, ladder id, 1). */
+int nemb200_replica_exchange(int n_chains, int ladder, int phase, int64_t round, uint64_t seed,
+                             int S, const double *d_gamma, int32_t *d_orders,
+                             double *d_curr_scores, uint32_t *d_curr_bits, int64_t *d_n_swaps,
+                             void *stream);
+
+/* ---- posterior edge frequencies: sum per-chain counts into int64 [S*S] (what the NCCL
+ *      all-reduce then sums across GPUs).  New in this build. */
+int nemb200_edge_counts_reduce(const uint32_t *d_edge_counts, int n_chains, int S,
+                               int64_t *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

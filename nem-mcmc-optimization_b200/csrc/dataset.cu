@@ -1,0 +1,148 @@
+// Resident dataset: replaces the score tables of the reference (nem.py:25-64, Q11: the reference
+// materialises S tables of S x E float64; everything the score needs is the 0/1 matrix D and A, B).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+void nemb200_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char *nemb200_last_error(void) { return g_err; }
+extern "C" int nemb200_version(void) { return NEMB200_VERSION; }
+
+namespace {
+
+struct Layout { size_t dcol, a_lut, lut, sumN, total; int W, n_mtiles; };
+Layout make_layout(int S, int E) {
+  Layout L;
+  L.W = (S + 31) / 32;
+  L.n_mtiles = (E + 127) / 128;
+  size_t off = 0;
+  L.dcol = off; off = align_up(off + (size_t)L.n_mtiles * 128 * L.W * 4, 1024);
+  L.a_lut = off; off = align_up(off + (size_t)L.n_mtiles * 128 * 128, 1024);
+  L.lut = off; off = align_up(off + 64 * 64 * 4, 1024);
+  L.sumN = off; off = align_up(off + 8, 1024);
+  L.total = off;
+  return L;
+}
+
+// bit i of dcol[e][w] = D[i][e]; rows e >= E are zero
+__global__ void k_pack_dcol(const uint8_t *D, int S, int E, int W, int E_pad, uint32_t *dcol) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E_pad) return;
+  for (int w = 0; w < W; ++w) {
+    uint32_t m = 0;
+    if (e < E)
+      for (int b = 0; b < 32 && w * 32 + b < S; ++b) m |= (uint32_t)(D[(size_t)(w * 32 + b) * E + e] != 0) << b;
+    dcol[(size_t)e * W + w] = m;
+  }
+}
+
+// u8 A-operand image, one 16 KB SWIZZLE_128B atom per 128 E-genes:
+//   a[e][k] = 2 if D[k][e] else 128 (k < S, e < E); a[e][S] = 128 for every row (exp-table base row); 0 elsewhere
+__global__ void k_build_aimg(const uint32_t *dcol, int S, int E, int W, int E_pad, uint8_t *img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (row e, 16-byte chunk c)
+  if (idx >= E_pad * 8) return;
+  int e = idx >> 3, c = idx & 7;
+  uint32_t bytes[4] = {0, 0, 0, 0};
+  for (int b = 0; b < 16; ++b) {
+    int k = c * 16 + b;
+    uint32_t v = 0;
+    if (k < S && e < E) v = ((dcol[(size_t)e * W + (k >> 5)] >> (k & 31)) & 1u) ? 2u : 128u;
+    else if (k == S) v = 128u;
+    bytes[b >> 2] |= v << ((b & 3) * 8);
+  }
+  int tile = e >> 7, r = e & 127;
+  size_t off = (size_t)tile * 16384 + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((c ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4 *>(img + off) = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
+}
+
+__global__ void k_sumN(const uint32_t *dcol, size_t n_words, double A, double *out) {
+  __shared__ unsigned long long sh[256];
+  unsigned long long c = 0;
+  for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) c += __popc(dcol[i]);
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = A * (double)sh[0];  // nem.py:62 summed over all E-genes
+}
+
+// lut[q][p] = 2^(alpha2*p + beta2*q - s) for p+q <= S (0 elsewhere), computed in fp64
+__global__ void k_build_lut(int S, double alpha2, double beta2, double s, float *lut) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 64) return;
+  int q = i >> 6, p = i & 63;
+  lut[i] = (p + q <= S) ? (float)exp2(alpha2 * p + beta2 * q - s) : 0.f;
+}
+
+}  // namespace
+
+extern "C" size_t nemb200_dataset_bytes(int S, int E) {
+  if (S < 1 || S > NEMB200_MAX_S || E < 1) return 0;
+  return make_layout(S, E).total;
+}
+
+extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A, double B, void *d_workspace,
+                                      size_t workspace_bytes, void *stream, nemb200_dataset **out) {
+  NEMB_REQUIRE(out != nullptr && d_D != nullptr && d_workspace != nullptr, "null argument");
+  NEMB_REQUIRE(S >= 1 && S <= NEMB200_MAX_S, "S must be in [1,%d] (got %d)", NEMB200_MAX_S, S);
+  NEMB_REQUIRE(E >= 1, "E must be >= 1 (got %d)", E);
+  NEMB_REQUIRE(isfinite(A) && isfinite(B), "A and B must be finite");
+  Layout L = make_layout(S, E);
+  NEMB_REQUIRE(workspace_bytes >= L.total, "dataset workspace too small: %zu < %zu", workspace_bytes, L.total);
+  NEMB_REQUIRE(((uintptr_t)d_workspace & 1023) == 0, "dataset workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  nemb200_dataset *h = (nemb200_dataset *)calloc(1, sizeof(nemb200_dataset));
+  NEMB_REQUIRE(h != nullptr, "out of host memory");
+  uint8_t *base = (uint8_t *)d_workspace;
+  h->S = S; h->E = E; h->W = L.W; h->KA = 1; h->n_mtiles = L.n_mtiles;
+  h->G = 256 / S < 16 ? 256 / S : 16;
+  h->A = A; h->B = B;
+  h->alpha2 = -A * NEMB200_LOG2E; h->beta2 = B * NEMB200_LOG2E;
+  h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_cnt = nullptr;
+  h->lut = (float *)(base + L.lut); h->sumN = (double *)(base + L.sumN);
+  // single-scale validity: largest log2-domain value over the lattice p+q<=S
+  double vmax = 0.0;
+  if (h->alpha2 > 0) vmax = fmax(vmax, h->alpha2 * S);
+  if (h->beta2 > 0) vmax = fmax(vmax, h->beta2 * S);
+  double s = ceil(vmax + log2((double)S + 1.0) - 126.0);
+  if (s < 0) s = 0;
+  h->scale = (int)s;
+  h->fixed_valid = s <= 100.0;
+  h->lut_valid = h->fixed_valid && S <= 63;
+  int E_pad = L.n_mtiles * 128;
+  k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
+  k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, h->a_lut);
+  k_sumN<<<1, 256, 0, st>>>(h->dcol, (size_t)E_pad * L.W, A, h->sumN);
+  k_build_lut<<<16, 256, 0, st>>>(S, h->alpha2, h->beta2, (double)h->scale, h->lut);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    free(h);
+    nemb200_set_error("dataset kernels failed to launch: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int nemb200_dataset_destroy(nemb200_dataset *h) {
+  free(h);
+  return 0;
+}
+
+extern "C" int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int n) {
+  NEMB_REQUIRE(h != nullptr && info != nullptr && n >= 8, "dataset_info needs a handle and 8 slots");
+  info[0] = h->S; info[1] = h->E; info[2] = h->W; info[3] = 128; info[4] = h->G;
+  info[5] = h->lut_valid; info[6] = h->scale; info[7] = h->n_mtiles;
+  return 0;
+}

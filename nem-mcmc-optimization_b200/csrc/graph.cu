@@ -1,0 +1,171 @@
+// Bit-packed graph kernels: transitive closure (utils.py:37-54), order -> graph
+// (nem_order_mcmc.py:54-77, 210-221) and the fp64 popcount witness score.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+// ---- closure: one warp per graph, rows in registers, row k broadcast by shuffle ----------------
+template <int TW>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_closure(const uint32_t *__restrict__ adj, int n, int S,
+                                                                 uint32_t *__restrict__ out) {
+  const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= n) return;
+  const uint32_t *src = adj + (size_t)g * S * TW;
+  uint32_t r[TW][TW];
+#pragma unroll
+  for (int t = 0; t < TW; ++t) {
+    int row = t * 32 + lane;
+#pragma unroll
+    for (int w = 0; w < TW; ++w) {
+      uint32_t v = row < S ? src[row * TW + w] : 0u;
+      int hi = S - w * 32;                       // mask bits >= S
+      if (hi < 32) v &= hi <= 0 ? 0u : ((1u << hi) - 1u);
+      r[t][w] = v;
+    }
+  }
+  warp_closure<TW>(r, S);
+  uint32_t *dst = out + (size_t)g * S * TW;
+#pragma unroll
+  for (int t = 0; t < TW; ++t) {
+    int row = t * 32 + lane;
+    if (row < S) {
+#pragma unroll
+      for (int w = 0; w < TW; ++w) dst[row * TW + w] = r[t][w];
+    }
+  }
+}
+
+// ---- order -> graph: one warp per chain ----------------------------------------------------------
+// row(label at position p) = labels at positions > p  (get_permissible_parents :63-64 transposed to the
+// reference's dag orientation), optionally & candidate mask, optionally closed.
+template <int TW>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_order_to_graph(const int32_t *__restrict__ orders, int n, int S,
+                                                                        int rule, const uint32_t *__restrict__ cand,
+                                                                        int use_nem, uint32_t *__restrict__ out) {
+  __shared__ uint32_t sh[kWarpsPerBlock][128 * 4];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kWarpsPerBlock + wib;
+  if (c >= n) return;
+  const int32_t *ord = orders + (size_t)c * S;
+  int labels[TW];
+#pragma unroll
+  for (int t = 0; t < TW; ++t) labels[t] = t * 32 + lane < S ? ord[t * 32 + lane] : -1;
+  uint32_t r[TW][TW];
+  warp_graph_from_labels<TW>(labels, S, rule, cand, use_nem, sh[wib], r);
+  uint32_t *dst = out + (size_t)c * S * TW;
+#pragma unroll
+  for (int t = 0; t < TW; ++t) {
+    int row = t * 32 + lane;
+    if (row < S) {
+#pragma unroll
+      for (int w = 0; w < TW; ++w) dst[row * TW + w] = r[t][w];
+    }
+  }
+}
+
+// ---- witness score: AND + popcount on bit columns, exact two-pass logsumexp in fp64 -------------
+// grid (E chunks, graphs); independent of the tensor-core path (no MMA, no table, no shared layout).
+__global__ void __launch_bounds__(256) k_score_witness(const uint32_t *__restrict__ phi, const uint32_t *__restrict__ dcol,
+                                                       int S, int W, int E, double A, double B, double *__restrict__ part) {
+  __shared__ uint32_t anc[128 * 4];
+  __shared__ int cnt[128];
+  __shared__ double red[256];
+  const int g = blockIdx.y;
+  const uint32_t *rows = phi + (size_t)g * S * W;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    uint32_t m[4] = {0, 0, 0, 0};
+    int c = 0;
+    for (int a = 0; a < S; ++a) {
+      uint32_t bit = ((rows[a * W + (j >> 5)] >> (j & 31)) & 1u) | (a == j ? 1u : 0u);
+      m[a >> 5] |= bit << (a & 31);
+      c += (int)bit;
+    }
+    for (int w = 0; w < W; ++w) anc[j * W + w] = m[w];
+    cnt[j] = c;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    uint32_t d[4] = {0, 0, 0, 0};
+    for (int w = 0; w < W; ++w) d[w] = dcol[(size_t)e * W + w];
+    double m = 0.0;
+    for (int j = 0; j < S; ++j) {
+      int p = 0;
+      for (int w = 0; w < W; ++w) p += __popc(anc[j * W + w] & d[w]);
+      double v = -A * p + B * (cnt[j] - p);
+      m = fmax(m, v);
+    }
+    double s = exp(-m);
+    for (int j = 0; j < S; ++j) {
+      int p = 0;
+      for (int w = 0; w < W; ++w) p += __popc(anc[j * W + w] & d[w]);
+      s += exp(-A * p + B * (cnt[j] - p) - m);
+    }
+    acc += m + log(s);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[(size_t)g * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void k_witness_finalize(const double *part, int n_chunks, const double *sumN, int n, double *scores) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  double v = *sumN;
+  for (int c = 0; c < n_chunks; ++c) v += part[(size_t)g * n_chunks + c];
+  scores[g] = v;
+}
+
+}  // namespace
+
+int launch_closure(const uint32_t *adj, int n, int S, uint32_t *out, cudaStream_t st) {
+  if (n == 0) return 0;
+  int W = (S + 31) / 32, grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  switch (W) {
+    case 1: k_closure<1><<<grid, kWarpsPerBlock * 32, 0, st>>>(adj, n, S, out); break;
+    case 2: k_closure<2><<<grid, kWarpsPerBlock * 32, 0, st>>>(adj, n, S, out); break;
+    case 3: k_closure<3><<<grid, kWarpsPerBlock * 32, 0, st>>>(adj, n, S, out); break;
+    default: k_closure<4><<<grid, kWarpsPerBlock * 32, 0, st>>>(adj, n, S, out); break;
+  }
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_order_to_graph(const int32_t *orders, int n, int S, int rule, const uint32_t *cand, int use_nem, uint32_t *out,
+                          cudaStream_t st) {
+  if (n == 0) return 0;
+  int W = (S + 31) / 32, grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  switch (W) {
+    case 1: k_order_to_graph<1><<<grid, kWarpsPerBlock * 32, 0, st>>>(orders, n, S, rule, cand, use_nem, out); break;
+    case 2: k_order_to_graph<2><<<grid, kWarpsPerBlock * 32, 0, st>>>(orders, n, S, rule, cand, use_nem, out); break;
+    case 3: k_order_to_graph<3><<<grid, kWarpsPerBlock * 32, 0, st>>>(orders, n, S, rule, cand, use_nem, out); break;
+    default: k_order_to_graph<4><<<grid, kWarpsPerBlock * 32, 0, st>>>(orders, n, S, rule, cand, use_nem, out); break;
+  }
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// the witness needs n * kWitnessChunks doubles of scratch
+static constexpr int kWitnessChunks = 8;
+size_t score_witness_workspace_bytes(int n) { return sizeof(double) * (size_t)n * kWitnessChunks; }
+
+int launch_score_witness(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, cudaStream_t st) {
+  if (n == 0) return 0;
+  int chunks = kWitnessChunks;
+  double *part = reinterpret_cast<double *>(ws);
+  for (int g0 = 0; g0 < n; g0 += 32768) {  // gridDim.y limit 65535
+    int ng = n - g0 < 32768 ? n - g0 : 32768;
+    dim3 grid(chunks, ng);
+    k_score_witness<<<grid, 256, 0, st>>>(phi + (size_t)g0 * h->S * h->W, h->dcol, h->S, h->W, h->E, h->A, h->B,
+                                          part + (size_t)g0 * chunks);
+  }
+  k_witness_finalize<<<(n + 255) / 256, 256, 0, st>>>(part, chunks, h->sumN, n, scores);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

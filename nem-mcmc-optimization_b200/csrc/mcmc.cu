@@ -1,0 +1,367 @@
+// Device-resident order-MCMC: replaces the loop of NEMOrderMCMC.method (nem_order_mcmc.py:272-302).
+// Per iteration three launches, all captured into a CUDA graph so the host never synchronises:
+//   propose (get_new_order :231-255 + order->graph :54-77,210-221)  ->  batched score  ->
+//   accept (accepting :224-229 + best-so-far bookkeeping :290-302 + posterior edge counts).
+// Randomness: Philox4x32-10, key = seed, counter = (iteration lo, iteration hi, global chain id, 0);
+// word 0 -> swap vs adjacent, words 1,2 -> positions, word 3 -> accept uniform.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+struct McmcWs {
+  long long *iter_a;      // iteration index read by propose (written by accept)
+  long long *iter_b;      // iteration index read by accept (written by propose)
+  long long *since;       // [n] iteration at which the current graph became current (edge-count bookkeeping)
+  int32_t *prop_orders;   // [n][S]
+  uint32_t *prop_bits;    // [n][S][W]
+  double *prop_scores;    // [n]
+  void *score_ws;
+  size_t score_ws_bytes;
+};
+
+size_t carve(const nemb200_dataset *h, int n, void *base, McmcWs *w) {
+  size_t off = 0;
+  uint8_t *b = (uint8_t *)base;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  size_t o_iter = take(16), o_since = take(8 * (size_t)n), o_po = take(4 * (size_t)n * h->S),
+         o_pb = take(4 * (size_t)n * h->S * h->W), o_ps = take(8 * (size_t)n);
+  size_t sws = score_tc_workspace_bytes(h, n), wws = score_witness_workspace_bytes(n);
+  if (wws > sws) sws = wws;
+  size_t o_sw = take(sws);
+  if (w) {
+    w->iter_a = (long long *)(b + o_iter); w->iter_b = w->iter_a + 1;
+    w->since = (long long *)(b + o_since); w->prop_orders = (int32_t *)(b + o_po);
+    w->prop_bits = (uint32_t *)(b + o_pb); w->prop_scores = (double *)(b + o_ps);
+    w->score_ws = b + o_sw; w->score_ws_bytes = sws;
+  }
+  return off;
+}
+
+__global__ void k_mcmc_init(long long *iter_a, long long *iter_b, long long *since, int n, long long iter0) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { *iter_a = iter0; *iter_b = iter0; }
+  if (i < n) since[i] = iter0;
+}
+
+template <int TW>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_mcmc_propose(
+    const int32_t *__restrict__ orders, int n, int S, const long long *iter_a, long long *iter_b, uint64_t seed,
+    uint32_t chain_offset, unsigned long long swap_prob_u33, int rule, const uint32_t *__restrict__ cand, int use_nem,
+    int init, int32_t *__restrict__ prop_orders, uint32_t *__restrict__ prop_bits) {
+  __shared__ uint32_t sh[kWarpsPerBlock][128 * 4];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kWarpsPerBlock + wib;
+  const long long t = *iter_a;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *iter_b = t;
+  if (c >= n) return;
+  int si = -1, sj = -1;
+  if (!init) {
+    uint32_t ctr[4] = {(uint32_t)t, (uint32_t)((unsigned long long)t >> 32), chain_offset + (uint32_t)c, 0u};
+    philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    if ((unsigned long long)ctr[0] < swap_prob_u33) {  // swap two distinct uniform positions (:238-244)
+      si = (int)__umulhi(ctr[1], (uint32_t)S);
+      sj = (int)__umulhi(ctr[2], (uint32_t)(S - 1));
+      if (sj >= si) ++sj;
+    } else {                                            // swap adjacent positions (:245-251)
+      si = (int)__umulhi(ctr[1], (uint32_t)(S - 1));
+      sj = si + 1;
+    }
+  }
+  const int32_t *ord = orders + (size_t)c * S;
+  int labels[TW];
+#pragma unroll
+  for (int tt = 0; tt < TW; ++tt) {
+    int p = tt * 32 + lane;
+    int src = p == si ? sj : (p == sj ? si : p);
+    labels[tt] = p < S ? ord[src] : -1;
+    if (p < S) prop_orders[(size_t)c * S + p] = labels[tt];
+  }
+  uint32_t r[TW][TW];
+  warp_graph_from_labels<TW>(labels, S, rule, cand, use_nem, sh[wib], r);
+  uint32_t *dst = prop_bits + (size_t)c * S * TW;
+#pragma unroll
+  for (int tt = 0; tt < TW; ++tt) {
+    int row = tt * 32 + lane;
+    if (row < S) {
+#pragma unroll
+      for (int w = 0; w < TW; ++w) dst[row * TW + w] = r[tt][w];
+    }
+  }
+}
+
+// counts[a*S+b] += k for every edge a->b of `bits`
+__device__ __forceinline__ void warp_add_edges(uint32_t *counts, const uint32_t *bits, int S, int W, uint32_t k, int lane) {
+  for (int cell = lane; cell < S * S; cell += 32) {
+    int a = cell / S, b = cell - a * S;
+    if ((bits[a * W + (b >> 5)] >> (b & 31)) & 1u) counts[cell] += k;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_mcmc_accept(
+    int n, int S, int W, long long *iter_a, const long long *iter_b, long long iter0, long long burn_in, uint64_t seed,
+    uint32_t chain_offset, const double *__restrict__ gamma, int init, const int32_t *__restrict__ prop_orders,
+    const uint32_t *__restrict__ prop_bits, const double *__restrict__ prop_scores, int32_t *__restrict__ orders,
+    double *__restrict__ curr_scores, uint32_t *__restrict__ curr_bits, double *__restrict__ best_scores,
+    int32_t *__restrict__ best_orders, uint32_t *__restrict__ best_bits, long long *__restrict__ accept,
+    uint32_t *__restrict__ edge_counts, long long *__restrict__ since, double *__restrict__ trace) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kWarpsPerBlock + wib;
+  const long long t = *iter_b;
+  if (!init && blockIdx.x == 0 && threadIdx.x == 0) *iter_a = t + 1;
+  if (c >= n) return;
+  const double ll = prop_scores[c];
+  bool acc, better;
+  if (init) {
+    acc = true; better = true;
+  } else {
+    uint32_t ctr[4] = {(uint32_t)t, (uint32_t)((unsigned long long)t >> 32), chain_offset + (uint32_t)c, 0u};
+    philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u = ((double)ctr[3] + 0.5) * (1.0 / 4294967296.0);
+    const double curr = curr_scores[c];
+    acc = u < exp(gamma[c] * (ll - curr));            // accepting(), :224-229
+    better = acc && ll > best_scores[c];              // :290-292
+    if (trace != nullptr && lane == 0) {  // [iteration][0: proposed score, 1: current score after the decision][chain]
+      trace[((size_t)(t - iter0) * 2 + 0) * n + c] = ll;
+      trace[((size_t)(t - iter0) * 2 + 1) * n + c] = acc ? ll : curr;
+    }
+  }
+  if (!acc) return;
+  const int nw = S * W;
+  if (!init && edge_counts != nullptr) {
+    // the graph being replaced was current for iterations [since, t-1]; count the post-burn-in ones
+    long long from = since[c] > burn_in ? since[c] : burn_in;
+    if (t > from) warp_add_edges(edge_counts + (size_t)c * S * S, curr_bits + (size_t)c * nw, S, W, (uint32_t)(t - from), lane);
+    __syncwarp();
+    if (lane == 0) since[c] = t;
+  }
+  for (int i = lane; i < S; i += 32) {
+    int v = prop_orders[(size_t)c * S + i];
+    orders[(size_t)c * S + i] = v;
+    if (better) best_orders[(size_t)c * S + i] = v;
+  }
+  for (int i = lane; i < nw; i += 32) {
+    uint32_t v = prop_bits[(size_t)c * nw + i];
+    curr_bits[(size_t)c * nw + i] = v;
+    if (better) best_bits[(size_t)c * nw + i] = v;
+  }
+  if (lane == 0) {
+    curr_scores[c] = ll;
+    if (better) best_scores[c] = ll;
+    if (!init) accept[c] += 1;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_mcmc_flush(int n, int S, int W, long long t_end, long long burn_in,
+                                                                    const uint32_t *__restrict__ curr_bits,
+                                                                    uint32_t *__restrict__ edge_counts,
+                                                                    long long *__restrict__ since) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kWarpsPerBlock + wib;
+  if (c >= n) return;
+  long long from = since[c] > burn_in ? since[c] : burn_in;
+  if (t_end > from)
+    warp_add_edges(edge_counts + (size_t)c * S * S, curr_bits + (size_t)c * S * W, S, W, (uint32_t)(t_end - from), lane);
+  __syncwarp();
+  if (lane == 0) since[c] = t_end;
+}
+
+// ---- replica exchange (nem_order_mcmc.py:326-340): one warp per neighbouring pair ----------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_replica_exchange(
+    int n_chains, int ladder, int phase, long long round, uint64_t seed, int S, int W, const double *__restrict__ gamma,
+    int32_t *__restrict__ orders, double *__restrict__ curr_scores, uint32_t *__restrict__ curr_bits,
+    long long *__restrict__ n_swaps) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pairs_per_ladder = ladder / 2;  // upper bound; odd phases may have one fewer
+  const int pid = blockIdx.x * kWarpsPerBlock + wib;
+  const int lad = pid / pairs_per_ladder, k = pid - lad * pairs_per_ladder;
+  const int i = lad * ladder + 2 * k + (phase ? 1 : 0), j = i + 1;
+  if (lad * ladder >= n_chains || j >= (lad + 1) * ladder || j >= n_chains) return;
+  uint32_t ctr[4] = {(uint32_t)round, (uint32_t)((unsigned long long)round >> 32), (uint32_t)pid, 1u};
+  philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u = ((double)ctr[3] + 0.5) * (1.0 / 4294967296.0);
+  const double si = curr_scores[i], sj = curr_scores[j];
+  const double delta = gamma[i] * sj - gamma[i] * si + gamma[j] * si - gamma[j] * sj;  // :333
+  if (!(u < exp(-delta))) return;
+  for (int q = lane; q < S; q += 32) {
+    int a = orders[(size_t)i * S + q], b = orders[(size_t)j * S + q];
+    orders[(size_t)i * S + q] = b; orders[(size_t)j * S + q] = a;
+  }
+  for (int q = lane; q < S * W; q += 32) {
+    uint32_t a = curr_bits[(size_t)i * S * W + q], b = curr_bits[(size_t)j * S * W + q];
+    curr_bits[(size_t)i * S * W + q] = b; curr_bits[(size_t)j * S * W + q] = a;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    curr_scores[i] = sj; curr_scores[j] = si;
+    if (n_swaps) atomicAdd((unsigned long long *)n_swaps, 1ull);
+  }
+}
+
+__global__ void k_edge_reduce(const uint32_t *__restrict__ counts, int n, int cells, long long *__restrict__ out) {
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= cells) return;
+  long long s = 0;
+  for (int c = 0; c < n; ++c) s += counts[(size_t)c * cells + cell];
+  out[cell] = s;
+}
+
+}  // namespace
+
+extern "C" size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_chains) {
+  if (!h || n_chains < 0) return 0;
+  return carve(h, n_chains, nullptr, nullptr);
+}
+
+static int score_dispatch(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
+                          int impl, cudaStream_t st) {
+  if (impl == NEMB200_SCORE_WITNESS || (impl == NEMB200_SCORE_AUTO && h->S < 8)) {
+    NEMB_REQUIRE(ws_bytes >= score_witness_workspace_bytes(n), "score workspace too small");
+    return launch_score_witness(h, phi, n, scores, ws, st);
+  }
+  return launch_score_tc(h, phi, n, scores, ws, ws_bytes, impl, st);
+}
+
+extern "C" size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs) {
+  if (!h || n_graphs < 0) return 0;
+  size_t a = score_tc_workspace_bytes(h, n_graphs), b = score_witness_workspace_bytes(n_graphs);
+  return a > b ? a : b;
+}
+
+extern "C" int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_phi_bits, int n_graphs, double *d_scores,
+                                   void *d_workspace, size_t workspace_bytes, int impl, void *stream) {
+  NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
+  NEMB_REQUIRE(n_graphs == 0 || (d_phi_bits && d_scores && d_workspace), "null device pointer");
+  return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream);
+}
+
+extern "C" int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_t *d_out_bits, void *stream) {
+  NEMB_REQUIRE(S >= 1 && S <= NEMB200_MAX_S, "S must be in [1,%d] (got %d)", NEMB200_MAX_S, S);
+  NEMB_REQUIRE(n_graphs >= 0 && (n_graphs == 0 || (d_adj_bits && d_out_bits)), "bad arguments");
+  return launch_closure(d_adj_bits, n_graphs, S, d_out_bits, (cudaStream_t)stream);
+}
+
+extern "C" int nemb200_order_to_graph(const int32_t *d_orders, int n_chains, int S, int rule, const uint32_t *d_cand_bits,
+                                      int use_nem, uint32_t *d_out_bits, void *stream) {
+  NEMB_REQUIRE(S >= 1 && S <= NEMB200_MAX_S, "S must be in [1,%d] (got %d)", NEMB200_MAX_S, S);
+  NEMB_REQUIRE(rule == NEMB200_RULE_FULL || (rule == NEMB200_RULE_MASKED && d_cand_bits), "MASKED rule needs a candidate mask");
+  NEMB_REQUIRE(n_chains >= 0 && (n_chains == 0 || (d_orders && d_out_bits)), "bad arguments");
+  return launch_order_to_graph(d_orders, n_chains, S, rule, d_cand_bits, use_nem, d_out_bits, (cudaStream_t)stream);
+}
+
+extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters, int64_t iter0, int64_t burn_in,
+                                const double *d_gamma, double swap_prob, uint64_t seed, uint32_t chain_offset, int rule,
+                                const uint32_t *d_cand_bits, int use_nem, int resume, int score_impl, int32_t *d_orders,
+                                double *d_curr_scores, uint32_t *d_curr_bits, double *d_best_scores, int32_t *d_best_orders,
+                                uint32_t *d_best_bits, int64_t *d_accept, uint32_t *d_edge_counts, double *d_score_trace,
+                                void *d_workspace, size_t workspace_bytes, void *stream) {
+  NEMB_REQUIRE(h != nullptr, "null dataset");
+  NEMB_REQUIRE(n >= 0 && n_iters >= 0, "negative sizes");
+  if (n == 0) return 0;
+  NEMB_REQUIRE(h->S >= 2, "order-MCMC needs S >= 2");
+  NEMB_REQUIRE(d_gamma && d_orders && d_curr_scores && d_curr_bits && d_best_scores && d_best_orders && d_best_bits &&
+                   d_accept && d_workspace,
+               "null device pointer");
+  NEMB_REQUIRE(rule == NEMB200_RULE_FULL || (rule == NEMB200_RULE_MASKED && d_cand_bits), "MASKED rule needs a candidate mask");
+  NEMB_REQUIRE(workspace_bytes >= carve(h, n, nullptr, nullptr), "mcmc workspace too small");
+  NEMB_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "mcmc workspace must be 256-byte aligned");
+  NEMB_REQUIRE(swap_prob >= 0.0 && swap_prob <= 1.0, "swap_prob must be in [0,1]");
+  cudaStream_t st = (cudaStream_t)stream;
+  McmcWs w;
+  carve(h, n, d_workspace, &w);
+  const int S = h->S, W = h->W;
+  const unsigned long long sp = swap_prob >= 1.0 ? 0x100000000ull : (unsigned long long)(swap_prob * 4294967296.0 + 0.5);
+  const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock, thr = kWarpsPerBlock * 32;
+
+  auto propose = [&](int init) -> int {
+    switch (W) {
+      case 1: k_mcmc_propose<1><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+      case 2: k_mcmc_propose<2><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+      case 3: k_mcmc_propose<3><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+      default: k_mcmc_propose<4><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+    }
+    NEMB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  };
+  auto step = [&](int init) -> int {
+    int rc = propose(init);
+    if (rc) return rc;
+    rc = score_dispatch(h, w.prop_bits, n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, st);
+    if (rc) return rc;
+    k_mcmc_accept<<<grid, thr, 0, st>>>(n, S, W, w.iter_a, w.iter_b, iter0, burn_in, seed, chain_offset, d_gamma, init,
+                                        w.prop_orders, w.prop_bits, w.prop_scores, d_orders, d_curr_scores, d_curr_bits,
+                                        d_best_scores, d_best_orders, d_best_bits, (long long *)d_accept, d_edge_counts,
+                                        w.since, d_score_trace);
+    NEMB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  };
+
+  k_mcmc_init<<<(n + 255) / 256, 256, 0, st>>>(w.iter_a, w.iter_b, w.since, n, iter0);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  if (!resume) {
+    int rc = step(1);  // method(): score of the start order (:258), best = current
+    if (rc) return rc;
+  }
+  // capture kUnroll iterations into a CUDA graph (no host sync per iteration); the legacy NULL stream
+  // cannot be captured, so it falls back to direct launches
+  constexpr int kUnroll = 8;
+  int64_t done = 0;
+  if (st != nullptr && n_iters >= 2 * kUnroll) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    NEMB_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int u = 0; u < kUnroll && rc == 0; ++u) rc = step(0);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != 0 || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      if (rc == 0) nemb200_set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+      return rc ? rc : -2;
+    }
+    NEMB_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    for (; done + kUnroll <= n_iters; done += kUnroll) {
+      cudaError_t le = cudaGraphLaunch(exec, st);
+      if (le != cudaSuccess) {
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        nemb200_set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(le));
+        return -2;
+      }
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+  }
+  for (; done < n_iters; ++done) {
+    int rc = step(0);
+    if (rc) return rc;
+  }
+  if (d_edge_counts != nullptr) {
+    k_mcmc_flush<<<grid, thr, 0, st>>>(n, S, W, iter0 + n_iters, burn_in, d_curr_bits, d_edge_counts, w.since);
+    NEMB_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int nemb200_replica_exchange(int n_chains, int ladder, int phase, int64_t round, uint64_t seed, int S,
+                                        const double *d_gamma, int32_t *d_orders, double *d_curr_scores,
+                                        uint32_t *d_curr_bits, int64_t *d_n_swaps, void *stream) {
+  NEMB_REQUIRE(n_chains >= 0 && ladder >= 2 && S >= 1 && S <= NEMB200_MAX_S, "bad arguments");
+  if (n_chains < 2) return 0;
+  NEMB_REQUIRE(d_gamma && d_orders && d_curr_scores && d_curr_bits, "null device pointer");
+  int ladders = (n_chains + ladder - 1) / ladder, pairs = ladders * (ladder / 2);
+  k_replica_exchange<<<(pairs + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      n_chains, ladder, phase & 1, round, seed, S, (S + 31) / 32, d_gamma, d_orders, d_curr_scores, d_curr_bits,
+      (long long *)d_n_swaps);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int nemb200_edge_counts_reduce(const uint32_t *d_edge_counts, int n_chains, int S, int64_t *d_out, void *stream) {
+  NEMB_REQUIRE(d_edge_counts && d_out && n_chains >= 0 && S >= 1 && S <= NEMB200_MAX_S, "bad arguments");
+  int cells = S * S;
+  k_edge_reduce<<<(cells + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_edge_counts, n_chains, cells, (long long *)d_out);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,308 @@
+"""Torch-side plumbing of the B200 NEM hot path: device memory, streams and the batched entry points
+(`Dataset.score_graphs`, `closure`, `Dataset.run_chains`) that the drop-in `NEM` / `NEMOrderMCMC`
+classes call.  PyTorch only owns tensors and streams; all compute is in libnemb200.so.
+
+Bit-packed graph layout (include/nemb200.h): uint32 [n][S][W], bit b of word w of row a set iff
+edge a -> 32*w+b, i.e. the reference's ``dag`` orientation (nem_order_mcmc.py:213).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+RULE_FULL, RULE_MASKED = 0, 1
+SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4}
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.NemB200Error("nem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def words(S: int) -> int:
+    return (S + 31) // 32
+
+
+def pack_adj(adj) -> np.ndarray:
+    """(n,S,S) or (S,S) 0/1 array -> uint32 bit rows (n,S,W) (host, numpy)."""
+    a = np.asarray(adj)
+    single = a.ndim == 2
+    if single:
+        a = a[None]
+    n, S, S2 = a.shape
+    assert S == S2
+    W = words(S)
+    buf = np.zeros((n, S, W * 32), dtype=np.uint8)
+    buf[:, :, :S] = a != 0
+    bits = np.packbits(buf, axis=-1, bitorder="little").view("<u4").reshape(n, S, W)
+    return bits[0] if single else bits
+
+
+def unpack_adj(bits, S: int) -> np.ndarray:
+    """uint32 bit rows (n,S,W) -> (n,S,S) uint8."""
+    b = np.ascontiguousarray(np.asarray(bits).astype("<u4", copy=False))
+    single = b.ndim == 2
+    if single:
+        b = b[None]
+    n = b.shape[0]
+    u8 = b.view(np.uint8).reshape(n, S, -1)
+    out = np.unpackbits(u8, axis=-1, bitorder="little")[:, :, :S]
+    return out[0] if single else out
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(stream: torch.cuda.Stream):
+    return C.c_void_p(stream.cuda_stream)
+
+
+def _bits_to_device(graphs, S, device) -> torch.Tensor:
+    """Accept (n,S,S) 0/1 arrays, (n,S,W) uint32 bit rows (numpy) or int32 CUDA tensors of bit rows."""
+    if isinstance(graphs, torch.Tensor):
+        t = graphs
+        if t.dtype not in (torch.int32, torch.uint32):
+            raise TypeError("device graphs must be bit rows stored as int32")
+        return t.to(device).contiguous().view(torch.int32)
+    a = np.asarray(graphs)
+    if a.dtype == np.uint32:  # uint32 arrays are always bit rows (n,S,W); adjacency uses any other dtype
+        bits = a if a.ndim == 3 else a[None]
+        if bits.shape[1:] != (S, words(S)):
+            raise ValueError(f"bit rows must have shape (n,{S},{words(S)}), got {bits.shape}")
+    else:
+        if a.ndim == 2:
+            a = a[None]
+        if a.shape[1:] != (S, S):
+            raise ValueError(f"adjacency must have shape (n,{S},{S}), got {a.shape}")
+        bits = pack_adj(a)
+    return torch.from_numpy(np.ascontiguousarray(bits).view(np.int32)).to(device, non_blocking=False)
+
+
+def closure(graphs, S: int | None = None, device=None, return_bits: bool = False):
+    """Transitive closure of a batch of graphs on the GPU (replaces utils.ancestor, utils.py:37-54)."""
+    device = _require_cuda(device)
+    if S is None:
+        S = np.asarray(graphs).shape[-2]
+    bits = _bits_to_device(graphs, S, device)
+    n = bits.shape[0]
+    out = torch.empty_like(bits)
+    st = torch.cuda.current_stream(device)
+    _lib.check(_lib.lib().nemb200_closure_u32(_ptr(bits), n, S, _ptr(out), _stream_ptr(st)))
+    if return_bits:
+        return out
+    return unpack_adj(out.cpu().numpy().view(np.uint32), S)
+
+
+@dataclass
+class ChainResult:
+    best_scores: np.ndarray      # (n,)
+    best_orders: np.ndarray      # (n,S)
+    best_graphs: np.ndarray      # (n,S,S) uint8, [a][b]=1 iff a->b
+    curr_scores: np.ndarray
+    curr_orders: np.ndarray
+    accept_counts: np.ndarray    # (n,)
+    edge_counts: np.ndarray | None   # (S,S) int64 summed over chains (post burn-in)
+    score_trace: np.ndarray | None   # (n_iters, 2, n): proposed score, current score after the decision
+    n_iters: int
+
+
+class Dataset:
+    """Device-resident observed knock-down matrix D (S x E, 0/1) + the error constants A, B (nem.py:17-18).
+    Replaces the S x S x E score tables of the reference (nem.py:36-64)."""
+
+    def __init__(self, D, A: float, B: float, device=None):
+        self.device = _require_cuda(device)
+        L = _lib.lib()
+        if isinstance(D, torch.Tensor):
+            d = (D != 0).to(torch.uint8).to(self.device).contiguous()
+        else:
+            d = torch.from_numpy(np.ascontiguousarray((np.asarray(D) != 0).astype(np.uint8))).to(self.device)
+        self.S, self.E = int(d.shape[0]), int(d.shape[1])
+        self.A, self.B = float(A), float(B)
+        nbytes = L.nemb200_dataset_bytes(self.S, self.E)
+        if nbytes == 0:
+            raise _lib.NemB200Error(f"unsupported dataset shape S={self.S}, E={self.E} (1 <= S <= 128)")
+        # over-allocate so the workspace can be 1024-byte aligned
+        self._ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+        off = (-self._ws.data_ptr()) % 1024
+        self._ws_ptr = self._ws.data_ptr() + off
+        self._stream = torch.cuda.Stream(self.device)  # non-default stream: CUDA-graph capture needs one
+        h = C.c_void_p()
+        st = torch.cuda.current_stream(self.device)
+        _lib.check(L.nemb200_dataset_create(_ptr(d), self.S, self.E, self.A, self.B, C.c_void_p(self._ws_ptr),
+                                            nbytes, _stream_ptr(st), C.byref(h)))
+        self._h = h
+        st.synchronize()  # d (the uint8 copy) may be freed after this
+        info = (C.c_int64 * 8)()
+        _lib.check(L.nemb200_dataset_info(self._h, info, 8))
+        self.W, self.graphs_per_tile, self.lut_valid, self.scale_log2, self.n_mtiles = (
+            int(info[2]), int(info[4]), bool(info[5]), int(info[6]), int(info[7]))
+        self._score_ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().nemb200_dataset_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- batched score -------------------------------------------------------------------------
+    def _score_workspace(self, n):
+        need = _lib.lib().nemb200_score_workspace_bytes(self._h, n)
+        if self._score_ws is None or self._score_ws.numel() < need:
+            self._score_ws = torch.empty(max(need, 1), dtype=torch.uint8, device=self.device)
+        return self._score_ws, need
+
+    def score_bits(self, bits: torch.Tensor, impl="auto", out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+        """Score bit-packed graphs already on the device; returns a float64 CUDA tensor (no sync)."""
+        n = int(bits.shape[0])
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=self.device)
+        ws, need = self._score_workspace(n)
+        st = stream or torch.cuda.current_stream(self.device)
+        _lib.check(_lib.lib().nemb200_score_batch(self._h, _ptr(bits), n, _ptr(out), _ptr(ws), ws.numel(),
+                                                  SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl),
+                                                  _stream_ptr(st)))
+        return out
+
+    def score_graphs(self, graphs, impl="auto", close: bool = False) -> np.ndarray:
+        """NEM log-likelihood ratio of each graph (host in, host out): the reference's
+        compute_ll_ratios + calculate_ll for binary weights (nem.py:72-86 as driven at :132-142).
+        graphs: (n,S,S) 0/1 adjacency ([a][b]=1 iff a->b) or (n,S,W) uint32 bit rows.
+        close=True applies the transitive closure first (create_nem, nem_order_mcmc.py:216-221)."""
+        bits = _bits_to_device(graphs, self.S, self.device)
+        if close:
+            st = torch.cuda.current_stream(self.device)
+            _lib.check(_lib.lib().nemb200_closure_u32(_ptr(bits), bits.shape[0], self.S, _ptr(bits), _stream_ptr(st)))
+        return self.score_bits(bits, impl).cpu().numpy()
+
+    def order_graphs(self, orders, rule=RULE_FULL, cand=None, use_nem=True) -> torch.Tensor:
+        """Bit rows of the graph each order induces (device tensor)."""
+        o = torch.as_tensor(np.ascontiguousarray(np.asarray(orders, dtype=np.int32))).to(self.device)
+        if o.ndim == 1:
+            o = o[None]
+        n = o.shape[0]
+        cand_t = None if cand is None else _bits_to_device(np.asarray(cand)[None], self.S, self.device)[0].contiguous()
+        out = torch.empty((n, self.S, self.W), dtype=torch.int32, device=self.device)
+        st = torch.cuda.current_stream(self.device)
+        _lib.check(_lib.lib().nemb200_order_to_graph(_ptr(o), n, self.S, int(rule), _ptr(cand_t), int(bool(use_nem)),
+                                                     _ptr(out), _stream_ptr(st)))
+        return out
+
+    # ---- order-MCMC --------------------------------------------------------------------------------
+    def run_chains(self, orders0, n_iters: int, gamma, swap_prob: float = 0.95, seed: int = 1234,
+                   chain_offset: int = 0, rule: int = RULE_FULL, cand=None, use_nem: bool = True,
+                   burn_in: int = 0, edge_counts: bool = True, trace: bool = False, impl="auto",
+                   state: "ChainState | None" = None) -> "ChainState":
+        """Run independent order-MCMC chains on the device (the loop of NEMOrderMCMC.method,
+        nem_order_mcmc.py:272-302).  orders0: (n,S) start orders; gamma: scalar or (n,).
+        Returns the device-resident ChainState (call .result() for host arrays)."""
+        if state is None:
+            state = ChainState(self, orders0, gamma, edge_counts, chain_offset=chain_offset, seed=seed,
+                               rule=rule, cand=cand, use_nem=use_nem, burn_in=burn_in)
+        state.run(n_iters, swap_prob=swap_prob, trace=trace, impl=impl)
+        return state
+
+
+class ChainState:
+    """All per-chain MCMC state, resident in HBM (caller-owned buffers of nemb200_mcmc_run)."""
+
+    def __init__(self, ds: Dataset, orders0, gamma, edge_counts=True, chain_offset=0, seed=1234, rule=RULE_FULL,
+                 cand=None, use_nem=True, burn_in=0):
+        self.ds = ds
+        dev = ds.device
+        o = np.ascontiguousarray(np.asarray(orders0, dtype=np.int32))
+        if o.ndim == 1:
+            o = o[None]
+        n, S = o.shape
+        if S != ds.S:
+            raise ValueError(f"orders have {S} entries, dataset has S={ds.S}")
+        if not all(np.array_equal(np.sort(r), np.arange(S)) for r in o[: min(n, 64)]):
+            raise ValueError("each start order must be a permutation of range(S)")
+        self.n, self.S, self.W = n, S, ds.W
+        self.orders = torch.from_numpy(o).to(dev)
+        g = np.broadcast_to(np.asarray(gamma, dtype=np.float64), (n,)).copy()
+        self.gamma = torch.from_numpy(g).to(dev)
+        self.curr_scores = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.curr_bits = torch.zeros((n, S, self.W), dtype=torch.int32, device=dev)
+        self.best_scores = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.best_orders = torch.zeros((n, S), dtype=torch.int32, device=dev)
+        self.best_bits = torch.zeros((n, S, self.W), dtype=torch.int32, device=dev)
+        self.accept = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.edge_counts = torch.zeros((n, S * S), dtype=torch.int32, device=dev) if edge_counts else None
+        self.cand = None if cand is None else _bits_to_device(np.asarray(cand)[None], S, dev)[0].contiguous()
+        self.rule, self.use_nem, self.burn_in = int(rule), bool(use_nem), int(burn_in)
+        self.seed, self.chain_offset = int(seed), int(chain_offset)
+        self.iters_done = 0
+        self.started = False
+        self.trace = None
+        need = _lib.lib().nemb200_mcmc_workspace_bytes(ds._h, n)
+        self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        self._ws_off = (-self._ws.data_ptr()) % 256
+        self._ws_bytes = need
+
+    def _call(self, n_iters, swap_prob, tr, impl):
+        ds = self.ds
+        _lib.check(_lib.lib().nemb200_mcmc_run(
+            ds._h, self.n, int(n_iters), self.iters_done, self.burn_in, _ptr(self.gamma), float(swap_prob),
+            C.c_uint64(self.seed), C.c_uint32(self.chain_offset), self.rule, _ptr(self.cand), int(self.use_nem),
+            int(self.started), SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl),
+            _ptr(self.orders), _ptr(self.curr_scores), _ptr(self.curr_bits), _ptr(self.best_scores),
+            _ptr(self.best_orders), _ptr(self.best_bits), _ptr(self.accept), _ptr(self.edge_counts), _ptr(tr),
+            C.c_void_p(self._ws.data_ptr() + self._ws_off), self._ws_bytes, _stream_ptr(ds._stream)))
+        self.started = True
+        self.iters_done += int(n_iters)
+
+    def run(self, n_iters: int, swap_prob=0.95, trace=False, impl="auto"):
+        """Advance every chain by n_iters iterations (asynchronous; no host sync)."""
+        ds = self.ds
+        tr = torch.empty((n_iters, 2, self.n), dtype=torch.float64, device=ds.device) if trace and n_iters > 0 else None
+        st = ds._stream
+        st.wait_stream(torch.cuda.current_stream(ds.device))
+        with torch.cuda.stream(st):
+            if not self.started:  # method(): score of the start orders first (nem_order_mcmc.py:258)
+                self._call(0, swap_prob, None, impl)
+                self.init_scores = self.curr_scores.clone()
+            self._call(n_iters, swap_prob, tr, impl)
+        torch.cuda.current_stream(ds.device).wait_stream(st)
+        self.trace = tr
+        return self
+
+    def replica_exchange(self, ladder: int, phase: int, round_idx: int) -> torch.Tensor:
+        """Neighbour swaps inside ladders of `ladder` consecutive chains (nem_order_mcmc.py:326-340)."""
+        ds = self.ds
+        nsw = torch.zeros(1, dtype=torch.int64, device=ds.device)
+        st = torch.cuda.current_stream(ds.device)
+        _lib.check(_lib.lib().nemb200_replica_exchange(self.n, int(ladder), int(phase), int(round_idx),
+                                                       C.c_uint64(self.seed), self.S, _ptr(self.gamma),
+                                                       _ptr(self.orders), _ptr(self.curr_scores), _ptr(self.curr_bits),
+                                                       _ptr(nsw), _stream_ptr(st)))
+        return nsw
+
+    def edge_count_matrix(self) -> torch.Tensor:
+        """int64 (S,S) device tensor: per-chain posterior edge counts summed over this GPU's chains."""
+        ds = self.ds
+        out = torch.zeros(self.S * self.S, dtype=torch.int64, device=ds.device)
+        if self.edge_counts is not None:
+            st = torch.cuda.current_stream(ds.device)
+            _lib.check(_lib.lib().nemb200_edge_counts_reduce(_ptr(self.edge_counts), self.n, self.S, _ptr(out),
+                                                             _stream_ptr(st)))
+        return out.view(self.S, self.S)
+
+    def result(self) -> ChainResult:
+        S = self.S
+        ec = self.edge_count_matrix().cpu().numpy() if self.edge_counts is not None else None
+        return ChainResult(
+            best_scores=self.best_scores.cpu().numpy(), best_orders=self.best_orders.cpu().numpy(),
+            best_graphs=unpack_adj(self.best_bits.cpu().numpy().view(np.uint32), S),
+            curr_scores=self.curr_scores.cpu().numpy(), curr_orders=self.orders.cpu().numpy(),
+            accept_counts=self.accept.cpu().numpy(), edge_counts=ec,
+            score_trace=None if self.trace is None else self.trace.cpu().numpy(), n_iters=self.iters_done)

@@ -1,0 +1,134 @@
+"""Drop-in for the reference's ``utils.py`` on the hot path: same names, argument meaning and
+return types.  Graph/score arithmetic runs on the GPU through libnemb200; data synthesis, CSV
+reading and small order utilities are host-side input preparation exactly as in the reference."""
+from __future__ import annotations
+
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+
+
+# ---- data synthesis (host side input preparation, utils.py:5-35) --------------------------------
+def create_connection_mat(s_mat):
+    """utils.py:5-13: conn[j][i] = 1 iff i == j or s_mat[i][j] == 1."""
+    s = np.asarray(s_mat)
+    n = s.shape[1]
+    conn = np.eye(n)
+    conn[np.nonzero(s.T == 1)] = 1
+    return conn
+
+
+def create_real_knockdown_mat(s_mat, e_arr):
+    """utils.py:15-23: column k is the reachability column of the S-gene E-gene k hangs on."""
+    conn = create_connection_mat(s_mat)
+    return np.ascontiguousarray(conn[np.asarray(e_arr, dtype=np.int64)].T)
+
+
+def create_observed_knockdown_mat(knockdown_mat, alpha, beta, seed=42):
+    """utils.py:25-35: one Mersenne-Twister uniform per cell in row-major order; false positives with
+    probability alpha, false negatives with probability beta (the module-global ``random`` is
+    re-seeded, as the reference does)."""
+    random.seed(seed)
+    kd = np.asarray(knockdown_mat)
+    u = np.fromiter((random.random() for _ in range(kd.size)), dtype=np.float64, count=kd.size).reshape(kd.shape)
+    flipped = kd.copy()
+    flipped[(kd == 0) & (u < alpha)] = 1
+    flipped[(kd == 1) & (u < beta)] = 0
+    return flipped
+
+
+# ---- closure (GPU) ---------------------------------------------------------------------------------
+def ancestor(incidence):
+    """utils.py:37-54 - transitive closure of an S x S incidence matrix, computed by the bit-packed
+    CUDA closure kernel.  Boolean semantics (the reference's int64 path count wraps for dense
+    S >= 66; this does not)."""
+    inc = np.asarray(incidence)
+    out = engine.closure((inc > 0).astype(np.uint8)[None], S=inc.shape[0])[0]
+    return out.astype(int)
+
+
+def initial_order_guess(observed_knockdown_mat):
+    """utils.py:56-64."""
+    return np.argsort(-np.sum(np.asarray(observed_knockdown_mat), axis=1))
+
+
+# ---- score helpers (GPU) -----------------------------------------------------------------------------
+def _rows_ll_ratios(U, n_parents, parent_weights, reduced_score_tables, device):
+    """cell[i] = U[i] + sum_j log(1 - w_ij + w_ij exp(row_ij)) for explicit table rows (torch CUDA ops;
+    compatibility form for callers that pass raw rows - the batched hot path is Dataset.score_graphs)."""
+    cell = torch.as_tensor(np.asarray(U, dtype=np.float64)).to(device).clone()
+    for i in range(len(parent_weights)):
+        k = int(n_parents[i])
+        if k == 0:
+            continue
+        rows = torch.as_tensor(np.asarray(reduced_score_tables[i], dtype=np.float64)[:k]).to(device)
+        w = torch.as_tensor(np.asarray(parent_weights[i], dtype=np.float64)[:k]).to(device)[:, None]
+        cell[i] += torch.log(1.0 - w + w * torch.exp(rows)).sum(dim=0)
+    return cell
+
+
+def compute_ll_ratios(n_parents, U, parent_weights, reduced_score_tables):
+    """utils.py:66-82 (Eq. 13): (S+1, E) cell log-ratios for real-valued parent weights."""
+    dev = engine._require_cuda()
+    return _rows_ll_ratios(U, n_parents, parent_weights, reduced_score_tables, dev).cpu().numpy()
+
+
+def cell_ll(cell_ratios, want_weights=False, device=None):
+    """Column logaddexp + sum on the GPU (nemb200_cell_ll)."""
+    import ctypes as C
+    dev = engine._require_cuda(device)
+    cell = cell_ratios if isinstance(cell_ratios, torch.Tensor) else torch.as_tensor(
+        np.ascontiguousarray(np.asarray(cell_ratios, dtype=np.float64)))
+    cell = cell.to(dev, torch.float64).contiguous()
+    rows, E = cell.shape
+    L = _lib.lib()
+    ws = torch.empty(max(L.nemb200_cell_ll_workspace_bytes(E), 8), dtype=torch.uint8, device=dev)
+    ll = torch.empty(1, dtype=torch.float64, device=dev)
+    ow = torch.empty_like(cell) if want_weights else None
+    st = torch.cuda.current_stream(dev)
+    _lib.check(L.nemb200_cell_ll(engine._ptr(cell), rows, E, engine._ptr(ow), engine._ptr(ll), engine._ptr(ws),
+                                 ws.numel(), engine._stream_ptr(st)))
+    return (ow.cpu().numpy() if want_weights else None), float(ll.item())
+
+
+def compute_ll(cell_ratios):
+    """utils.py:84-94 (Eq. 14): sum over E-genes of logaddexp over the S+1 rows."""
+    return cell_ll(cell_ratios)[1]
+
+
+# ---- input formats / small host utilities ---------------------------------------------------------------
+def read_csv_to_adj(pathname):
+    """utils.py:96-118.  Line 1 ``S,E``; edge lines ``i,j``; one line of E attachment indices;
+    last line ``alpha,beta``.  (The reference detects the end-node line as the first line without
+    exactly two fields, so E == 2 is ambiguous - SURVEY Q14; here the last two lines are always the
+    end nodes and the errors.)"""
+    with open(os.path.join(os.getcwd(), pathname), "r") as f:
+        lines = [ln.strip() for ln in f if ln.strip()]
+    num_s, num_e = (int(x) for x in lines[0].split(","))
+    adj = np.zeros((num_s, num_s), dtype=int)
+    for ln in lines[1:-2]:
+        a, b = (int(x) for x in ln.split(","))
+        adj[a, b] = 1
+    end_nodes = np.array([int(x) for x in lines[-2].split(",")])
+    errors = np.array([float(x) for x in lines[-1].split(",")])
+    return adj, end_nodes, errors, num_s, num_e
+
+
+def transitive_reduction(adj_matrix):
+    """utils.py:120-129 (host; result post-processing)."""
+    a = np.array(adj_matrix, copy=True)
+    n = a.shape[0]
+    for k in range(n):
+        via = np.outer(a[:, k] != 0, a[k, :] != 0)
+        np.fill_diagonal(via, False)
+        a[via] = 0
+    return a
+
+
+def hamming_distance(mat_a, mat_b):
+    """utils.py:148-149."""
+    return np.sum(np.abs(np.asarray(mat_a) - np.asarray(mat_b)))

@@ -1,0 +1,376 @@
+"""GPU parity tests (run on the B200 box): CUDA path through the C ABI vs the CPU oracle on the same
+seeded inputs, the reference's golden fixtures, and size-independent properties at full sizes."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, nem_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TC_IMPLS = ["lut", "ex2", "ex2_2pass"]
+REL_TC = 1e-6       # fp32 epilogue; north-star tolerance is 1e-4 * |score|
+REL_WITNESS = 1e-11  # fp64 popcount witness
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nem_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return nem_b200
+
+
+def rand_dags(rng, n, S, p=0.25, closed=True):
+    out = np.zeros((n, S, S), dtype=np.uint8)
+    for g in range(n):
+        order = rng.permutation(S)
+        pos = np.empty(S, dtype=int); pos[order] = np.arange(S)
+        a = ((pos[:, None] < pos[None, :]) & (rng.random((S, S)) < p)).astype(np.uint8)
+        out[g] = c_oracle.closure(a) if closed else a
+    return out
+
+
+# ------------------------------------------------------------------------------------------ closure
+@pytest.mark.parametrize("n", range(20))
+def test_closure_golden_networks(nb, golden, n):
+    arr, _ = golden
+    got = nb.closure(arr[f"red{n}"][None])[0]
+    assert np.array_equal(got, arr[f"adj{n}"])
+    assert np.array_equal(nb.utils.ancestor(arr[f"red{n}"]), arr[f"anc_red{n}"])
+
+
+@pytest.mark.parametrize("S", [1, 2, 9, 10, 20, 30, 31, 32, 33, 50, 64, 65, 96, 100, 128])
+def test_closure_random_vs_oracle(nb, S):
+    rng = np.random.default_rng(S)
+    n = 300
+    dags = rand_dags(rng, n, S, p=0.15, closed=False)
+    cyc = (rng.random((40, S, S)) < 0.05).astype(np.uint8)  # general digraphs (cycles allowed)
+    for g in cyc:
+        np.fill_diagonal(g, 0)
+    batch = np.concatenate([dags, cyc])
+    got = nb.closure(batch)
+    for g in range(len(batch)):
+        assert np.array_equal(got[g], c_oracle.closure(batch[g])), (S, g)
+    assert np.array_equal(nb.closure(got), got)  # idempotent
+
+
+def test_closure_dense_and_empty(nb, golden):
+    arr, _ = golden
+    tri = np.triu(np.ones((70, 70), dtype=np.uint8), 1)
+    assert np.array_equal(nb.closure(tri[None])[0], arr["anc_tri70"])
+    chain = np.zeros((100, 100), dtype=np.uint8)
+    chain[np.arange(99), np.arange(1, 100)] = 1
+    assert np.array_equal(nb.closure(chain[None])[0], np.triu(np.ones((100, 100), dtype=np.uint8), 1))
+    assert nb.closure(np.zeros((0, 10, 10), dtype=np.uint8), S=10).shape == (0, 10, 10)
+
+
+def test_closure_large_batch_properties(nb):
+    """BASELINE config 5 size: 65536 random DAGs at S=30: idempotent, superset, acyclic-preserving."""
+    rng = np.random.default_rng(5)
+    S, n = 30, 65536
+    pos = np.argsort(rng.random((n, S)), axis=1)
+    a = ((pos[:, :, None] < pos[:, None, :]) & (rng.random((n, S, S)) < 0.12)).astype(np.uint8)
+    bits = nb.pack_adj(a)
+    c1 = nb.closure(bits, S=S, return_bits=True)
+    c2 = nb.closure(c1, S=S, return_bits=True)
+    assert torch.equal(c1, c2)
+    h = c1.cpu().numpy().view(np.uint32)
+    assert np.all((h & bits) == bits)
+    closed = nb.unpack_adj(h, S)
+    assert not closed[:, np.arange(S), np.arange(S)].any()
+    for g in rng.integers(0, n, 50):
+        assert np.array_equal(closed[g], c_oracle.closure(a[g]))
+
+
+# -------------------------------------------------------------------------------------------- score
+@pytest.mark.parametrize("n", range(20))
+def test_score_golden_obs_ll(nb, golden, n):
+    arr, meta = golden
+    info = meta["networks"][str(n)]
+    ds = nb.Dataset(arr[f"D{n}"], info["A"], info["B"])
+    adj = arr[f"adj{n}"][None]
+    assert ds.score_graphs(adj, impl="witness")[0] == pytest.approx(info["obs_ll"], rel=REL_WITNESS)
+    for impl in TC_IMPLS:
+        assert ds.score_graphs(adj, impl=impl)[0] == pytest.approx(info["obs_ll"], rel=REL_TC), impl
+    assert ds.score_graphs(arr[f"red{n}"][None], close=True)[0] == pytest.approx(info["obs_ll"], rel=REL_TC)
+
+
+@pytest.mark.parametrize("n", [0, 5, 11, 12, 19])
+def test_score_golden_random_graphs(nb, golden, n):
+    arr, meta = golden
+    info = meta["networks"][str(n)]
+    ds = nb.Dataset(arr[f"D{n}"], info["A"], info["B"])
+    ref = np.array(info["rg_scores"])
+    assert np.allclose(ds.score_graphs(arr[f"rg{n}"], impl="witness"), ref, rtol=REL_WITNESS)
+    for impl in TC_IMPLS:
+        assert np.allclose(ds.score_graphs(arr[f"rg{n}"], impl=impl), ref, rtol=REL_TC), impl
+
+
+def test_score_noise_free_small_score(nb, golden):
+    """Noise-free data: the score is a small difference of large sums (network11: +14.4 vs |sum N| in the
+    thousands) - the north-star tolerance 1e-4*|score| must still hold."""
+    arr, meta = golden
+    info = meta["networks"]["11"]
+    ds = nb.Dataset(arr["real11"], info["A"], info["B"])
+    ref = c_oracle.score(arr["adj11"], arr["real11"], info["A"], info["B"])
+    for impl in ["witness"] + TC_IMPLS:
+        assert ds.score_graphs(arr["adj11"][None], impl=impl)[0] == pytest.approx(ref, abs=1e-4 * abs(ref)), impl
+
+
+@pytest.mark.parametrize("S,E,n", [(8, 40, 7), (10, 100, 33), (16, 257, 17), (20, 1000, 64), (30, 5000, 41),
+                                   (50, 1000, 23), (50, 10000, 12), (63, 700, 9), (64, 300, 9), (100, 1500, 7),
+                                   (128, 260, 5)])
+def test_score_synthetic_vs_oracle(nb, S, E, n):
+    rng = np.random.default_rng(S * 1000 + E)
+    _, _, D = orc.synth_dataset(S, E, seed=S + E)
+    A, B = orc.nem_constants(0.05, 0.1)
+    graphs = rand_dags(rng, n, S, p=0.3)
+    graphs[0] = 0                                                    # empty graph
+    graphs[1] = orc.order_to_graph(rng.permutation(S))               # full order graph
+    ref = c_oracle.score_batch(graphs, D, A, B, nthreads=8)
+    ds = nb.Dataset(D, A, B)
+    assert np.allclose(ds.score_graphs(graphs, impl="witness"), ref, rtol=REL_WITNESS)
+    impls = [i for i in TC_IMPLS if (i != "lut" or ds.lut_valid) and (i != "ex2" or S <= 54)]
+    assert impls
+    for impl in impls:
+        got = ds.score_graphs(graphs, impl=impl)
+        assert np.allclose(got, ref, rtol=REL_TC), (impl, np.abs(got / ref - 1).max())
+    assert np.allclose(ds.score_graphs(graphs), ref, rtol=REL_TC)    # auto
+
+
+@pytest.mark.parametrize("E", [1, 2, 127, 128, 129, 255, 256, 257])
+def test_score_ragged_E(nb, E):
+    S = 12
+    rng = np.random.default_rng(E)
+    D = (rng.random((S, E)) < 0.4).astype(np.uint8)
+    A, B = orc.nem_constants(0.05, 0.1)
+    graphs = rand_dags(rng, 19, S)
+    ref = c_oracle.score_batch(graphs, D, A, B)
+    ds = nb.Dataset(D, A, B)
+    for impl in ["witness"] + TC_IMPLS:
+        assert np.allclose(ds.score_graphs(graphs, impl=impl), ref, rtol=REL_TC), impl
+    assert ds.score_graphs(graphs[:0]).shape == (0,)
+    assert np.allclose(ds.score_graphs(graphs[:1]), ref[:1], rtol=REL_TC)
+
+
+def test_score_other_error_rates_and_unsupported(nb):
+    S, E = 40, 300
+    rng = np.random.default_rng(9)
+    D = (rng.random((S, E)) < 0.5).astype(np.uint8)
+    graphs = rand_dags(rng, 10, S)
+    for alpha, beta in [(0.01, 0.01), (0.2, 0.3), (0.001, 0.4)]:
+        A, B = orc.nem_constants(alpha, beta)
+        ds = nb.Dataset(D, A, B)
+        ref = c_oracle.score_batch(graphs, D, A, B)
+        assert np.allclose(ds.score_graphs(graphs), ref, rtol=REL_TC), (alpha, beta)
+        assert np.allclose(ds.score_graphs(graphs, impl="ex2_2pass"), ref, rtol=REL_TC)
+    with pytest.raises(nb._lib.NemB200Error):
+        nb.Dataset(np.zeros((129, 10), dtype=np.uint8), -1.0, -1.0)
+    ds = nb.Dataset(np.zeros((100, 10), dtype=np.uint8), *orc.nem_constants(0.05, 0.1))
+    with pytest.raises(nb._lib.NemB200Error):
+        ds.score_graphs(np.zeros((1, 100, 100), dtype=np.uint8), impl="lut")   # table epilogue needs S <= 63
+
+
+def test_score_full_size_c3_lut_vs_witness(nb):
+    """BASELINE config 3 shape (S=50, E=10k, 1024 graphs): tensor-core path vs the fp64 witness kernel
+    on the device, plus permutation invariance of the batch order."""
+    S, E, n = 50, 10000, 1024
+    rng = np.random.default_rng(3)
+    _, _, D = orc.synth_dataset(S, E, seed=0)
+    A, B = orc.nem_constants(0.05, 0.1)
+    ds = nb.Dataset(D, A, B)
+    orders = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
+    bits = ds.order_graphs(orders)
+    w = ds.score_bits(bits, impl="witness").cpu().numpy()
+    for impl in TC_IMPLS:
+        got = ds.score_bits(bits, impl=impl).cpu().numpy()
+        assert np.allclose(got, w, rtol=REL_TC), impl
+    perm = torch.from_numpy(rng.permutation(n)).to(bits.device)
+    got_p = ds.score_bits(bits[perm].contiguous()).cpu().numpy()
+    assert np.array_equal(got_p, ds.score_bits(bits).cpu().numpy()[perm.cpu().numpy()])  # deterministic
+    for g in (0, 511, 1023):
+        assert w[g] == pytest.approx(c_oracle.score(orc.order_to_graph(orders[g]), D, A, B), rel=REL_WITNESS)
+
+
+# ------------------------------------------------------------------------------------ order -> graph
+@pytest.mark.parametrize("S", [2, 10, 33, 50, 100])
+def test_order_to_graph_vs_oracle(nb, S):
+    rng = np.random.default_rng(S)
+    D = (rng.random((S, 50)) < 0.5).astype(np.uint8)
+    ds = nb.Dataset(D, *orc.nem_constants(0.05, 0.1))
+    orders = np.stack([rng.permutation(S) for _ in range(37)]).astype(np.int32)
+    cand = (rng.random((S, S)) < 0.3).astype(np.uint8)
+    for rule, use_nem in itertools.product((0, 1), (False, True)):
+        bits = ds.order_graphs(orders, rule=rule, cand=cand, use_nem=use_nem)
+        got = nb.unpack_adj(bits.cpu().numpy().view(np.uint32), S)
+        for c in range(len(orders)):
+            assert np.array_equal(got[c], orc.order_to_graph(orders[c], rule, cand, use_nem)), (rule, use_nem, c)
+
+
+# --------------------------------------------------------------------------------------------- MCMC
+def _compare_chain(res, c, ref, S, tol=1e-6):
+    assert res.accept_counts[c] == ref["n_accept"]
+    assert np.array_equal(res.curr_orders[c], ref["curr_order"])
+    assert np.array_equal(res.best_orders[c], ref["best_order"])
+    assert np.array_equal(res.best_graphs[c], ref["best_graph"])
+    assert res.best_scores[c] == pytest.approx(ref["best_score"], rel=tol)
+    assert res.curr_scores[c] == pytest.approx(ref["curr_score"], rel=tol)
+
+
+@pytest.mark.parametrize("S,E,rule,use_nem", [(10, 100, 0, True), (13, 126, 1, True), (13, 126, 1, False),
+                                              (20, 300, 0, False), (40, 200, 1, True)])
+def test_mcmc_trajectory_vs_oracle(nb, S, E, rule, use_nem):
+    """Same Philox draws as the oracle -> identical accept decisions, orders, best graphs and edge counts
+    (a decision can only differ if |u - rate| is below the fp32-epilogue error; seeds are fixed)."""
+    _, _, D = orc.synth_dataset(S, E, seed=7)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rng = np.random.default_rng(1)
+    cand = (rng.random((S, S)) < 0.4).astype(np.uint8)
+    n_chains, n_iter, burn = 6, 400, 50
+    gamma = 2.0 * S / E
+    orders0 = np.stack([rng.permutation(S) for _ in range(n_chains)]).astype(np.int32)
+    ds = nb.Dataset(D, A, B)
+    st = ds.run_chains(orders0, n_iter, gamma, swap_prob=0.9, seed=99, chain_offset=3, rule=rule, cand=cand,
+                       use_nem=use_nem, burn_in=burn, trace=True)
+    res = st.result()
+    total = np.zeros((S, S), dtype=np.int64)
+    for c in range(n_chains):
+        ref = c_oracle.mcmc_chain(D, A, B, orders0[c], n_iter, gamma, swap_prob=0.9, seed=99, chain=3 + c, rule=rule,
+                                  cand=cand, use_nem=use_nem, burn_in=burn, keep_scores=True)
+        _compare_chain(res, c, ref, S)
+        assert np.allclose(res.score_trace[:, 0, c], ref["all_score_list"][1:], rtol=1e-6)
+        assert st.init_scores[c].item() == pytest.approx(ref["all_score_list"][0], rel=1e-6)
+        total += ref["edge_counts"]
+    assert np.array_equal(res.edge_counts, total)
+    assert 0 < res.accept_counts.sum() < n_chains * n_iter
+
+
+def test_mcmc_resume_equals_single_run(nb):
+    S, E = 12, 150
+    _, _, D = orc.synth_dataset(S, E, seed=2)
+    A, B = orc.nem_constants(0.05, 0.1)
+    ds = nb.Dataset(D, A, B)
+    orders0 = np.stack([np.random.default_rng(c).permutation(S) for c in range(5)]).astype(np.int32)
+    a = ds.run_chains(orders0, 300, 0.2, seed=5, burn_in=100).result()
+    st = ds.run_chains(orders0, 120, 0.2, seed=5, burn_in=100)
+    st.run(37); st.run(143)
+    b = st.result()
+    for f in ("best_scores", "best_orders", "curr_orders", "accept_counts", "edge_counts", "curr_scores"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
+def test_mcmc_boltzmann_distribution(nb):
+    """S=4: visit frequencies over many device chains follow exp(gamma*score)."""
+    S, E = 4, 24
+    _, _, D = orc.synth_dataset(S, E, seed=1)
+    A, B = orc.nem_constants(0.05, 0.1)
+    gamma = 0.35
+    perms = list(itertools.permutations(range(S)))
+    sc = np.array([orc.score_counts(orc.order_to_graph(np.array(o)), D, A, B) for o in perms])
+    p = np.exp(gamma * (sc - sc.max())); p /= p.sum()
+    ds = nb.Dataset(D, A, B)
+    n = 8192
+    res = ds.run_chains(np.tile(np.arange(S, dtype=np.int32), (n, 1)), 60, gamma, swap_prob=0.5, seed=11).result()
+    idx = {o: k for k, o in enumerate(perms)}
+    freq = np.bincount([idx[tuple(int(x) for x in o)] for o in res.curr_orders], minlength=len(perms)) / n
+    assert np.abs(freq - p).max() < 0.02
+
+
+def test_replica_exchange_properties(nb):
+    S, E = 10, 100
+    _, _, D = orc.synth_dataset(S, E, seed=4)
+    ds = nb.Dataset(D, *orc.nem_constants(0.05, 0.1))
+    ladder, n = 10, 40
+    gam = np.tile((1 + 0.2 * np.arange(ladder)) * S / E, n // ladder)
+    st = ds.run_chains(np.stack([np.random.default_rng(c).permutation(S) for c in range(n)]).astype(np.int32), 50, gam)
+    before = st.curr_scores.clone()
+    orders_before = st.orders.clone()
+    nsw = int(st.replica_exchange(ladder, 0, 0).item())
+    after = st.curr_scores
+    # scores are permuted only inside pairs (2k, 2k+1); orders travel with their scores
+    for k in range(0, n, 2):
+        pair_b, pair_a = before[k:k + 2], after[k:k + 2]
+        same = torch.equal(pair_a, pair_b)
+        assert same or torch.equal(pair_a, pair_b.flip(0))
+        if not same:
+            assert torch.equal(st.orders[k], orders_before[k + 1]) and torch.equal(st.orders[k + 1], orders_before[k])
+    assert nsw == sum(int(not torch.equal(after[k:k + 2], before[k:k + 2])) for k in range(0, n, 2)) or nsw >= 0
+    sc = ds.score_bits(st.curr_bits).cpu().numpy()
+    assert np.allclose(sc, after.cpu().numpy(), rtol=1e-9)  # graphs travelled with the scores too
+
+
+# ------------------------------------------------------------------------------- drop-in classes
+@pytest.mark.parametrize("n", [0, 11, 12])
+def test_nem_class_golden(nb, golden, n):
+    arr, meta = golden
+    info = meta["networks"][str(n)]
+    model = nb.NEM(arr[f"adj{n}"].astype(int), arr[f"end{n}"], [info["alpha"], info["beta"]], info["S"], info["E"])
+    assert np.array_equal(model.observed_knockdown_mat, arr[f"D{n}"])
+    assert np.allclose(model.U, arr[f"U{n}"], rtol=1e-13, atol=1e-12)
+    assert model.obs_ll == pytest.approx(info["obs_ll"], rel=1e-12)
+    assert model.real_ll == pytest.approx(info["real_ll"], abs=1e-9)
+    assert model.A == info["A"] and model.B == info["B"]
+    # reference call sequence nem.py:132-142 through the mirrored methods
+    S = info["S"]
+    adj = arr[f"adj{n}"].astype(int); np.fill_diagonal(adj, 0)
+    parents = [[i for i in range(S) if adj[i][j] == 1] for j in range(S)]
+    w = [[1.0] * len(p) for p in parents]
+    tabs = model.get_score_tables(model.observed_knockdown_mat)
+    red = model.get_reduced_score_tables(tabs, parents)
+    ow, ll = model.calculate_ll(model.compute_ll_ratios(w, red, [len(p) for p in parents], model.U))
+    assert ll == pytest.approx(info["obs_ll"], rel=1e-12)
+    assert ow.shape == (S + 1, info["E"]) and np.allclose(ow.sum(axis=0), 1.0)
+    assert model.score_graphs(adj[None])[0] == pytest.approx(info["obs_ll"], rel=REL_TC)
+
+
+def test_mcmc_class_reference_smoke(nb):
+    """The reference's own smoke test (tests/utils.tests.py:30-49) through the drop-in classes."""
+    s_mat = np.array([[0, 1, 1, 0, 1], [0, 0, 1, 0, 1], [0, 0, 0, 0, 1], [0, 0, 1, 0, 1], [0, 0, 0, 0, 0]])
+    e_arr = [0, 1, 2, 3, 0, 1, 4, 2]
+    model = nb.NEM(adj_matrix=s_mat, end_nodes=e_arr, errors=[0.05, 0.1], num_s=5, num_e=8)
+    mc = nb.NEMOrderMCMC(model, perm_order=np.array([4, 3, 2, 1, 0]))
+    score, best_dag = mc.method(n_iterations=110, gamma=2.0 * 5 / 8, seed=42, verbose=False)
+    assert best_dag.shape == (5, 5) and np.isfinite(score)
+    assert len(mc.all_score_list) == 111 and len(mc.curr_score_list) == 111
+    assert score == max(mc.best_score_list) and score >= mc.all_score_list[0]
+    assert score == pytest.approx(c_oracle.score(best_dag.astype(np.uint8), model.observed_knockdown_mat.astype(np.uint8),
+                                                 model.A, model.B), rel=REL_TC)
+    ref = c_oracle.mcmc_chain(model.observed_knockdown_mat, model.A, model.B, [4, 3, 2, 1, 0], 110, 1.25, seed=42)
+    assert score == pytest.approx(ref["best_score"], rel=REL_TC)
+    assert np.array_equal(mc.best_order, ref["best_order"])
+    # multi-chain + masked rule + replica exchange run and return consistent results
+    s2, d2 = mc.method(n_iterations=64, gamma=1.25, seed=1, verbose=False, n_chains=32, rule="masked",
+                       cand=np.triu(np.ones((5, 5)), 1) + np.tril(np.ones((5, 5)), -1), use_nem=True)
+    assert s2 == pytest.approx(model.score_graphs(d2[None])[0], rel=REL_TC)
+    assert mc.edge_freq.shape == (5, 5) and mc.edge_freq.max() <= 1.0 + 1e-12
+    s3, rep = nb.replica_exchange_method(model, 6, 20, np.array([4, 3, 2, 1, 0]))
+    assert np.isfinite(s3) and rep.best_dag.shape == (5, 5)
+
+
+def test_mcmc_cell_ratio_methods(nb, golden):
+    """compute_cell_ratios / calculate_ll of the driver (nem_order_mcmc.py:79-93) incl. the expit quirk."""
+    from scipy.special import expit
+    arr, meta = golden
+    info = meta["networks"]["12"]
+    model = nb.NEM(arr["adj12"].astype(int), arr["end12"], [info["alpha"], info["beta"]], info["S"], info["E"])
+    order = arr["order0_12"]
+    mc = nb.NEMOrderMCMC(model, order)
+    S = info["S"]
+    rng = np.random.default_rng(0)
+    w = rng.normal(size=(S, S))
+    T, N, U = orc.score_tables(arr["D12"], info["A"], info["B"])
+    for use_expit in (True, False):
+        ww = expit(w) if use_expit else np.clip(w, 0.01, 0.99)
+        ref = U.copy()
+        for i in range(S):
+            for j in mc.parents_list[i]:
+                ref[i] += np.log(1.0 - ww[i][j] + ww[i][j] * np.exp(T[j]))
+        got = mc.compute_cell_ratios(w if use_expit else ww, expit=use_expit)
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)
+        mc.cell_ratios = got
+        ow, ll = mc.calculate_ll()
+        assert ll == pytest.approx(float(np.logaddexp.reduce(ref, axis=0).sum()), rel=1e-12)
+    assert nb.utils.compute_ll(ref) == pytest.approx(ll, rel=1e-12)
