@@ -51,7 +51,7 @@ def unpack_adj(bits, S: int) -> np.ndarray:
     if single:
         b = b[None]
     n = b.shape[0]
-    u8 = b.view(np.uint8).reshape(n, S, -1)
+    u8 = b.view(np.uint8).reshape(n, S, 4 * words(S))
     out = np.unpackbits(u8, axis=-1, bitorder="little")[:, :, :S]
     return out[0] if single else out
 
