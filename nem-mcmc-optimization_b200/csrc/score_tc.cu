@@ -14,38 +14,44 @@
 // lut[q][p] = 2^(alpha2*p + beta2*q - s).  Epilogue "LUT": one LDS + one FADD per (site, E-gene); an extra
 // K row adds the table's shared-memory base so the accumulator IS the address.  Epilogue "EX2": the same
 // accumulator is mapped linearly to the log2-domain value and exponentiated with ex2.approx (any S<=128);
-// "EX2_2PASS" subtracts the running maximum first (any dynamic range).
-// No B x S x E intermediate ever reaches HBM: per (graph, E-chunk) one double is written.
+// "EX2_2PASS" subtracts the running maximum first (any dynamic range).  For the headline shapes the
+// epilogue is compiled for a fixed S and splits each graph's sites between the two pipes (LSU table
+// look-ups and MUFU ex2) so that neither is the single limiter.
+// No B x S x E intermediate ever reaches HBM: per (graph, E-chunk, warpgroup) one double is written.
 //
-// Roles (320 threads): warp 0 = TMA producer (A tiles, 4-stage mbarrier ring), warp 1 = MMA issuer +
-// TMEM owner (2 x 256-column accumulators), warps 2-9 = two epilogue warpgroups that alternate tiles.
+// Roles (384 threads, no CTA-wide barrier in the main loop): warp 0 = TMA producer (A tiles, 4-stage
+// mbarrier ring), warp 1 = MMA issuer + TMEM owner (2 x 256-column accumulators), warps 2-3 = B-operand
+// expanders (double-buffered, run one work item ahead), warps 4-11 = two epilogue warpgroups that
+// alternate tiles.  Work items (N tile of graphs x chunk of E tiles) are statically strided over CTAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;
 constexpr int kStages = 4;
 constexpr int kTileBytes = 128 * 128;  // one operand atom: 128 rows x 128 B (SWIZZLE_128B)
 constexpr int kLutBytes = 64 * 256;
 constexpr int kMaxG = 16;
+constexpr int kBiasStride = 64;        // floats per graph in the bias array (S <= 128 uses two slots)
 
 // shared memory carve-up (offsets from the 1024-aligned base)
-constexpr int OFF_LUT = 0;                               // first: its base must be < 32 KB and 128-aligned
-constexpr int OFF_B = OFF_LUT + kLutBytes;               // 256 x 128 B
-constexpr int OFF_A = OFF_B + 2 * kTileBytes;            // kStages x 16 KB
-constexpr int OFF_BIAS = OFF_A + kStages * kTileBytes;   // 256 floats
-constexpr int OFF_ROWS = OFF_BIAS + 256 * 4;             // 1024 words of bit rows
-constexpr int OFF_RED = OFF_ROWS + 1024 * 4;             // 8 warps x 16 doubles
-constexpr int OFF_BAR = OFF_RED + 8 * kMaxG * 8;         // barriers + scalars
+constexpr int OFF_LUT = 0;                                  // first: its base must be < 32 KB and 128-aligned
+constexpr int OFF_B = OFF_LUT + kLutBytes;                  // 2 buffers x (256 x 128 B)
+constexpr int OFF_A = OFF_B + 2 * 2 * kTileBytes;           // kStages x 16 KB
+constexpr int OFF_BIAS = OFF_A + kStages * kTileBytes;      // 2 buffers x 1024 floats
+constexpr int OFF_ROWS = OFF_BIAS + 2 * 1024 * 4;           // 1024 words of bit rows (expander scratch)
+constexpr int OFF_RED = OFF_ROWS + 1024 * 4;                // 8 warps x 16 doubles
+constexpr int OFF_BAR = OFF_RED + 8 * kMaxG * 8;            // barriers + scalars
 constexpr int kSmemBytes = OFF_BAR + 256;
 
 struct Params {
   const uint32_t *phi;   // [n_graphs][S][W]
   const uint8_t *a_img;  // [n_mtiles][16 KB]
   const float *lut;      // [64][64]
-  double *partials;      // [n_ntiles*G][n_chunks]
-  unsigned int *counter; // work counter (zeroed before launch)
-  int n_graphs, S, W, E, G, n_ntiles, n_mtiles, tpc, n_chunks, n_items, nmma;
+  double *partials;      // [n_ntiles*G][n_chunks][2]
+  int n_graphs, S, W, E, G, n_ntiles, n_mtiles, tpc, n_chunks, n_items, nmma, ksteps;
   float k1;              // EX2: x = k1 * acc + bias_j
   float kc;              // EX2: bias_j = kc * c_j - s
   float scale;           // s
@@ -83,7 +89,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1<<16 |
 // SBO=(1024>>4)<<32 | version=1<<46 | layout SWIZZLE_128B=2<<61
@@ -102,6 +107,15 @@ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte_in_row) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((((byte_in_row >> 4) ^ (row & 7u)) << 4) | (byte_in_row & 15u));
 }
 
+#define TMEM_LD32(taddr, r)                                                                                            \
+  asm volatile(                                                                                                        \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                   \
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                        \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),     \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),          \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),         \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                       \
+      : "r"(taddr))
 #define TMEM_LD16(taddr, r)                                                                                         \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
@@ -134,15 +148,14 @@ __device__ __forceinline__ float log2_split(float x) {
 
 enum { EPI_LUT = 0, EPI_EX2 = 1, EPI_EX2_2PASS = 2 };
 
-// One graph's columns [col0, col0+S) of one accumulator tile for this thread's E-gene.
-// Returns log2( 2^-s + sum_j term_j ) + s  (i.e. log2 of 1 + sum_j 2^x_j).
+// ---- generic epilogue (runtime S): one graph's columns [0, S) of one accumulator tile ---------------
+// Returns log2( 1 + sum_j 2^x_j ) for this thread's E-gene.
 template <int EPI, int CH>
 __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *sBias, const Params &p) {
   static_assert(CH == 16 || CH == 8, "chunk");
   float acc0 = 0.f, acc1 = 0.f, m = 0.f;
   if (EPI == EPI_EX2_2PASS) {
-    // pass 1: running max of x_j (and 0 for the null site)
-    for (int c = 0; c < S; c += CH) {
+    for (int c = 0; c < S; c += CH) {  // pass 1: running max of x_j (and 0 for the null site)
       int cs = min(c, S - CH), skip = c - cs;
       uint32_t r[CH];
       if (CH == 16) TMEM_LD16(taddr + cs, r); else TMEM_LD8(taddr + cs, r);
@@ -162,7 +175,7 @@ __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *
       float v;
       if (EPI == EPI_LUT) v = lds_f32(r[i]);
       else if (EPI == EPI_EX2) v = ex2f(fmaf((float)(int)r[i], p.k1, sBias[cs + i]));
-      else v = ex2f(fmaf((float)(int)r[i], p.k1, sBias[cs + i]) - m);
+      else v = ex2f(fmaf((float)(int)r[i], p.k1, sBias[cs + i] - m));
       if (i >= skip) { if (i & 1) acc1 += v; else acc0 += v; }
     }
   }
@@ -171,22 +184,83 @@ __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *
 }
 
 template <int EPI>
+__device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const float *sBias, const Params &p, bool valid,
+                                                      int ng, double (&part)[kMaxG]) {
+  const int S = p.S;
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g) {
+    if (g < ng) {
+      float l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * S, S, sBias + g * kBiasStride * (S > 64 ? 2 : 1), p)
+                        : graph_lse2<EPI, 8>(taddr + g * S, S, sBias + g * kBiasStride, p);
+      if (valid) part[g] += (double)l;
+    }
+  }
+}
+
+// ---- specialised epilogue (compile-time S): straight-line code over the whole tile ----------------------
+// Sites j < NLUT of every graph go through the shared-memory exp table (LSU pipe), the others through
+// I2F + FFMA + ex2.approx (ALU/FMA/MUFU pipes).  The next 32 accumulator columns are prefetched from TMEM
+// while the current 32 are consumed.
+template <int S_T, int NLUT>
+__device__ __forceinline__ void tile_epilogue_static(uint32_t taddr, const float *sBias, const Params &p, bool valid,
+                                                     int ng, double (&part)[kMaxG]) {
+  constexpr int G = (256 / S_T) < kMaxG ? (256 / S_T) : kMaxG;
+  constexpr int NCOL = G * S_T;
+  constexpr int NCH = (NCOL + 31) / 32;
+  static_assert(NLUT % 4 == 0 || NLUT == S_T, "EX2 sites must start on a float4 boundary of the bias array");
+  uint32_t r[2][32];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float null_term = ex2f(-p.scale);
+  TMEM_LD32(taddr, r[0]);
+  tmem_wait_ld();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch + 1 < NCH) TMEM_LD32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int col = ch * 32 + i;
+      if (col < NCOL) {
+        const int g = col / S_T, j = col % S_T;
+        if (j == 0) { acc[0] = null_term; acc[1] = 0.f; acc[2] = 0.f; acc[3] = 0.f; }
+        float v;
+        if (j < NLUT) {
+          v = lds_f32(r[ch & 1][i]);
+        } else {
+          if (((j - NLUT) & 3) == 0) b4 = *reinterpret_cast<const float4 *>(sBias + g * kBiasStride + j);
+          const float b = ((j - NLUT) & 3) == 0 ? b4.x : (((j - NLUT) & 3) == 1 ? b4.y : (((j - NLUT) & 3) == 2 ? b4.z : b4.w));
+          v = ex2f(fmaf((float)(int)r[ch & 1][i], p.k1, b));
+        }
+        acc[j & 3] += v;
+        if (j == S_T - 1) {
+          const float l = log2_split((acc[0] + acc[1]) + (acc[2] + acc[3])) + p.scale;
+          if (valid && g < ng) part[g] += (double)l;
+        }
+      }
+    }
+    if (ch + 1 < NCH) tmem_wait_ld();
+  }
+}
+
+template <int EPI, int S_T, int NLUT>
 __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
-  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * kStages, bar_tfull = bar_empty + 8 * kStages,
-                 bar_tempty = bar_tfull + 16;
-  volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(bars + 2 * kStages + 4);
-  volatile int *s_item = reinterpret_cast<volatile int *>(bars + 2 * kStages + 5);
-  float *sBias = reinterpret_cast<float *>(smem + OFF_BIAS);
+  // barrier map: a_full[4] a_empty[4] t_full[2] t_empty[2] b_full[2] e_done[2]
+  const uint32_t bar_afull = sbase + OFF_BAR, bar_aempty = bar_afull + 8 * kStages, bar_tfull = bar_aempty + 8 * kStages,
+                 bar_tempty = bar_tfull + 16, bar_bfull = bar_tempty + 16, bar_edone = bar_bfull + 16;
+  volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(bars + 2 * kStages + 8);
   uint32_t *sRows = reinterpret_cast<uint32_t *>(smem + OFF_ROWS);
   double *sRed = reinterpret_cast<double *>(smem + OFF_RED);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_aempty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4);
+      mbar_init(bar_bfull + 8 * i, 2); mbar_init(bar_edone + 8 * i, 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -202,161 +276,211 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
   const int S = p.S, W = p.W, G = p.G;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32 (2<<4), A=B=U8 (0), K-major, N>>3 at 17, M>>4 at 24
   const uint32_t idesc = (2u << 4) | ((uint32_t)(p.nmma >> 3) << 17) | ((128u >> 4) << 24);
+  const int n_my_items = p.n_items > (int)blockIdx.x ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  uint32_t it = 0;  // running tile counter: identical sequence in every role
-  for (;;) {
-    if (threadIdx.x == 0) *s_item = (int)atomicAdd(p.counter, 1u);
-    __syncthreads();  // item id visible; previous item's B tile and accumulators are drained
-    const int item = *s_item;
-    if (item >= p.n_items) break;
-    const int chunk = item / p.n_ntiles, ntile = item % p.n_ntiles;
-    const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
-    const int g0 = ntile * G, ng = min(G, p.n_graphs - g0);
-
-    if (warp >= 2) {
-      // ---- expand the bit rows of this tile's graphs into the B operand (one thread per column)
-      const int te = threadIdx.x - 64;
-      const int nwords = ng * S * W;
-      for (int i = te; i < nwords; i += 256) sRows[i] = p.phi[(size_t)g0 * S * W + i];
-      epi_bar_sync();
-      const int gi = te / S, j = te - gi * S;
-      uint32_t anc[4] = {0u, 0u, 0u, 0u};
-      int cnt = 0;
-      const bool used = gi < ng;
-      if (used) {
-        const uint32_t *rows = sRows + gi * S * W;
-        const int jw = j >> 5, jb = j & 31;
-        for (int a = 0; a < S; ++a) {
-          uint32_t bit = ((rows[a * W + jw] >> jb) & 1u) | (a == j ? 1u : 0u);
-          anc[a >> 5] |= bit << (a & 31);
-          cnt += (int)bit;
+  if (warp == 0) {
+    // =============================== TMA producer: A tiles of every item, in order ===================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int k = 0; k < n_my_items; ++k) {
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;
+        const int chunk = item / p.n_ntiles;
+        const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
+        for (int t = 0; t < nt; ++t, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(bar_aempty + 8 * st, ph ^ 1u);
+          mbar_expect_tx(bar_afull + 8 * st, kTileBytes);
+          bulk_g2s(sbase + OFF_A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, kTileBytes, bar_afull + 8 * st);
         }
       }
-      uint8_t *brow = smem + OFF_B;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t half = (anc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-        uint4 v;
-        v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-        v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-        v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-        v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-        if (EPI == EPI_LUT && used && c == (S >> 4)) {
-          // extra K row S: B = lut_base/128, A = 128  ->  accumulator = shared address of lut[q][p]
-          uint32_t ext = ((sbase + OFF_LUT) >> 7) << ((S & 3) * 8);
-          int wsel = (S >> 2) & 3;
-          if (wsel == 0) v.x |= ext; else if (wsel == 1) v.y |= ext; else if (wsel == 2) v.z |= ext; else v.w |= ext;
-        }
-        *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)te, (uint32_t)c * 16u)) = v;
-      }
-      sBias[te] = p.kc * (float)cnt - p.scale;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();  // B tile + bias ready
-
-    if (warp == 0) {
-      if (lane == 0) {
-        for (int t = 0; t < nt; ++t) {
-          const uint32_t k = it + t, st = k % kStages, ph = (k / kStages) & 1u;
-          mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-          mbar_expect_tx(bar_full + 8 * st, kTileBytes);
-          bulk_g2s(sbase + OFF_A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, kTileBytes, bar_full + 8 * st);
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        for (int t = 0; t < nt; ++t) {
-          const uint32_t k = it + t, st = k % kStages, ph = (k / kStages) & 1u, buf = k & 1u, bph = (k >> 1) & 1u;
-          mbar_wait(bar_full + 8 * st, ph);
+  } else if (warp == 1) {
+    // =============================== MMA issuer =======================================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int k = 0; k < n_my_items; ++k) {
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;
+        const int chunk = item / p.n_ntiles;
+        const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
+        const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
+        mbar_wait(bar_bfull + 8 * bb, bbph);  // this item's B operand is expanded
+        const uint32_t b0 = sbase + OFF_B + bb * 2 * kTileBytes;
+        for (int t = 0; t < nt; ++t, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1u, buf = it & 1u, bph = (it >> 1) & 1u;
+          mbar_wait(bar_afull + 8 * st, ph);
           mbar_wait(bar_tempty + 8 * buf, bph ^ 1u);
           tc_fence_after();
-          const uint32_t a0 = sbase + OFF_A + st * kTileBytes, b0 = sbase + OFF_B;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
+          const uint32_t a0 = sbase + OFF_A + st * kTileBytes;
+          for (int ks = 0; ks < p.ksteps; ++ks)
             umma_i8(tmem_base + buf * 256u, umma_desc(a0 + ks * 32), umma_desc(b0 + ks * 32), idesc, ks > 0 ? 1u : 0u);
-          umma_commit(bar_empty + 8 * st);   // A slot reusable once these MMAs retire
+          umma_commit(bar_aempty + 8 * st);  // A slot reusable once these MMAs retire
           umma_commit(bar_tfull + 8 * buf);  // accumulator ready for the epilogue
         }
       }
-    } else {
-      // ---- epilogue: warpgroup wg handles tiles with (global tile index & 1) == wg
-      const int wg = (warp - 2) >> 2, quarter = warp & 3;
+    }
+  } else if (warp < 4) {
+    // =============================== B expanders (64 threads, one item ahead) ==========================
+    const int te = threadIdx.x - 64;
+    for (int k = 0; k < n_my_items; ++k) {
+      const int item = (int)blockIdx.x + k * (int)gridDim.x;
+      const int ntile = item % p.n_ntiles;
+      const int g0 = ntile * G, ng = min(G, p.n_graphs - g0);
+      const uint32_t bb = k & 1u;
+      if (k >= 2) mbar_wait(bar_edone + 8 * bb, ((k - 2) >> 1) & 1u);  // epilogue finished the item that used this buffer
+      const int nwords = ng * S * W;
+      for (int i = te; i < nwords; i += 64) sRows[i] = p.phi[(size_t)g0 * S * W + i];
+      asm volatile("bar.sync 3, 64;" ::: "memory");
+      uint8_t *brow = smem + OFF_B + bb * 2 * kTileBytes;
+      float *bias = reinterpret_cast<float *>(smem + OFF_BIAS) + bb * 1024;
+      const int bstride = kBiasStride * (S > 64 ? 2 : 1);
+      for (int col = te; col < 256; col += 64) {
+        const int gi = col / S, j = col - gi * S;
+        uint32_t anc[4] = {0u, 0u, 0u, 0u};
+        int cnt = 0;
+        const bool used = gi < ng;
+        if (used) {
+          const uint32_t *rows = sRows + gi * S * W;
+          const int jw = j >> 5, jb = j & 31;
+          for (int a = 0; a < S; ++a) {
+            uint32_t bit = ((rows[a * W + jw] >> jb) & 1u) | (a == j ? 1u : 0u);
+            anc[a >> 5] |= bit << (a & 31);
+            cnt += (int)bit;
+          }
+        }
+        // table look-up sites get the extra K row S: B = lut_base/128 (A holds 128 there), so that the
+        // accumulator is the shared-memory address of lut[q][p]; unused columns point at lut[0][0]
+        const bool lut_site = EPI == EPI_LUT && gi < G && (S_T == 0 || j < NLUT);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t half = (anc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+          uint4 v;
+          v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+          v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+          v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+          v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+          if (lut_site && c == (S >> 4)) {
+            uint32_t ext = ((sbase + OFF_LUT) >> 7) << ((S & 3) * 8);
+            int wsel = (S >> 2) & 3;
+            if (wsel == 0) v.x |= ext; else if (wsel == 1) v.y |= ext; else if (wsel == 2) v.z |= ext; else v.w |= ext;
+          }
+          *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
+        }
+        if (gi < G) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_bfull + 8 * bb);
+      asm volatile("bar.sync 3, 64;" ::: "memory");  // sRows is reused by the next item
+    }
+  } else {
+    // =============================== epilogue: warpgroup wg handles tiles with (tile index & 1) == wg ======
+    const int wg = (warp - 4) >> 2, quarter = warp & 3, tw = threadIdx.x - 128 - wg * 128;
+    uint32_t it = 0;
+    for (int k = 0; k < n_my_items; ++k) {
+      const int item = (int)blockIdx.x + k * (int)gridDim.x;
+      const int chunk = item / p.n_ntiles, ntile = item % p.n_ntiles;
+      const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
+      const int g0 = ntile * G, ng = min(G, p.n_graphs - g0);
+      const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
+      const float *bias = reinterpret_cast<const float *>(smem + OFF_BIAS) + bb * 1024;
+      mbar_wait(bar_bfull + 8 * bb, bbph);  // bias values of this item are written
       double part[kMaxG];
 #pragma unroll
       for (int g = 0; g < kMaxG; ++g) part[g] = 0.0;
-      for (int t = 0; t < nt; ++t) {
-        const uint32_t k = it + t, buf = k & 1u, bph = (k >> 1) & 1u;
+      for (int t = 0; t < nt; ++t, ++it) {
+        const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
         if ((int)buf != wg) continue;
         mbar_wait(bar_tfull + 8 * buf, bph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
         const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
-#pragma unroll
-        for (int g = 0; g < kMaxG; ++g) {
-          if (g < ng) {
-            float l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * S, S, sBias + g * S, p)
-                              : graph_lse2<EPI, 8>(taddr + g * S, S, sBias + g * S, p);
-            if (valid) part[g] += (double)l;
-          }
-        }
+        if constexpr (S_T > 0) tile_epilogue_static<S_T, NLUT>(taddr, bias, p, valid, ng, part);
+        else tile_epilogue_generic<EPI>(taddr, bias, p, valid, ng, part);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       }
-      // ---- per-item reduction over the 256 epilogue threads -> one double per (graph, chunk)
+      // ---- per-item reduction inside the warpgroup -> one double per (graph, chunk, warpgroup)
 #pragma unroll
       for (int g = 0; g < kMaxG; ++g) {
         if (g < ng) {
           double v = part[g];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) sRed[(warp - 2) * kMaxG + g] = v;
+          if (lane == 0) sRed[(warp - 4) * kMaxG + g] = v;
         }
       }
-      epi_bar_sync();
-      const int te = threadIdx.x - 64;
-      if (te < ng) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_edone + 8 * bb);  // bias / B buffer of this item may be recycled
+      if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tw < ng) {
         double v = 0.0;
-        for (int w8 = 0; w8 < 8; ++w8) v += sRed[w8 * kMaxG + te];
-        p.partials[(size_t)(g0 + te) * p.n_chunks + chunk] = v;
+        for (int w4 = 0; w4 < 4; ++w4) v += sRed[(wg * 4 + w4) * kMaxG + tw];
+        p.partials[((size_t)(g0 + tw) * p.n_chunks + chunk) * 2 + wg] = v;
       }
+      if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
     }
-    it += (uint32_t)nt;
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
-__global__ void k_finalize(const double *partials, int n_chunks, const double *sumN, int n_graphs, double *scores) {
+__global__ void k_finalize(const double *partials, int n_slots, const double *sumN, int n_graphs, double *scores) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_graphs) return;
   double v = 0.0;
-  for (int c = 0; c < n_chunks; ++c) v += partials[(size_t)g * n_chunks + c];
+  for (int c = 0; c < n_slots; ++c) v += partials[(size_t)g * n_slots + c];
   scores[g] = *sumN + NEMB200_LN2 * v;
 }
 
 struct Plan { int n_ntiles, tpc, n_chunks, n_items; };
-Plan make_plan(const nemb200_dataset *h, int n) {
+Plan make_plan(const nemb200_dataset *h, int n, int nsm) {
   Plan pl;
   pl.n_ntiles = (n + h->G - 1) / h->G;
-  // ~8 work items per SM, but at least 4 E tiles per item so the B expansion is amortised
-  long total = (long)pl.n_ntiles * h->n_mtiles;
-  int tpc = (int)(total / (148 * 8));
-  if (tpc < 4) tpc = 4;
-  if (tpc > h->n_mtiles) tpc = h->n_mtiles;
-  pl.n_chunks = (h->n_mtiles + tpc - 1) / tpc;
+  // Items are statically strided over the CTAs, so pick the E chunking whose item count wastes the least
+  // of the last round (items are equal-sized); prefer >= 6 tiles per item to amortise the B expansion.
+  int best_chunks = 1;
+  double best_cost = 1e30;
+  for (int nc = 1; nc <= h->n_mtiles; ++nc) {
+    int tpc = (h->n_mtiles + nc - 1) / nc;
+    int chunks = (h->n_mtiles + tpc - 1) / tpc;
+    if (chunks != nc) continue;
+    long items = (long)pl.n_ntiles * chunks;
+    long rounds = (items + nsm - 1) / nsm;
+    double cost = (double)rounds * (tpc + 1.5);  // +1.5 tiles of per-item overhead
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_chunks = chunks; }
+  }
+  pl.n_chunks = best_chunks;
   pl.tpc = (h->n_mtiles + pl.n_chunks - 1) / pl.n_chunks;
   pl.n_chunks = (h->n_mtiles + pl.tpc - 1) / pl.tpc;
   pl.n_items = pl.n_ntiles * pl.n_chunks;
   return pl;
 }
 
+int num_sms() {
+  static int nsm = 0;
+  if (nsm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
+      nsm = 148;
+  }
+  return nsm;
+}
+
+template <typename K>
+int launch_kernel(K kern, const Params &p, int grid, cudaStream_t st) {
+  NEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  kern<<<grid, kThreads, kSmemBytes, st>>>(p);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n) {
-  Plan pl = make_plan(h, n);
-  return 256 + sizeof(double) * (size_t)pl.n_ntiles * h->G * pl.n_chunks;
+  Plan pl = make_plan(h, n, num_sms());
+  return 256 + sizeof(double) * 2 * (size_t)pl.n_ntiles * h->G * pl.n_chunks;
 }
 
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
@@ -368,37 +492,45 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_EX2 || h->fixed_valid, "fixed-scale ex2 epilogue not valid for this dataset");
   NEMB_REQUIRE(ws_bytes >= score_tc_workspace_bytes(h, n), "score workspace too small");
   if (n == 0) return 0;
-  Plan pl = make_plan(h, n);
+  const int nsm = num_sms();
+  Plan pl = make_plan(h, n, nsm);
   Params p;
   p.phi = phi; p.a_img = h->a_lut; p.lut = h->lut;
-  p.counter = reinterpret_cast<unsigned int *>(ws);
   p.partials = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(ws) + 256);
   p.n_graphs = n; p.S = h->S; p.W = h->W; p.E = h->E; p.G = h->G;
   p.n_ntiles = pl.n_ntiles; p.n_mtiles = h->n_mtiles; p.tpc = pl.tpc; p.n_chunks = pl.n_chunks; p.n_items = pl.n_items;
   p.nmma = (h->G * h->S + 15) / 16 * 16;
+  p.ksteps = (h->S + (impl == NEMB200_SCORE_TC_LUT ? 1 : 0) + 31) / 32;
   // accumulator a = 4p + 256q = 256c - 252p  ->  x = alpha2*p + beta2*q = k1*a + kc*c
   const double kappa2 = h->alpha2 - h->beta2;
   p.k1 = (float)(-kappa2 / 252.0);
   p.kc = (float)(256.0 * kappa2 / 252.0 + h->beta2);
   p.scale = impl == NEMB200_SCORE_TC_EX2_2PASS ? 0.f : (float)h->scale;
-  NEMB_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));
-  int dev = 0, nsm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  int grid = pl.n_items < nsm ? pl.n_items : nsm;
-  auto launch = [&](auto kern) -> int {
-    NEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, st>>>(p);
-    NEMB_CHECK_CUDA(cudaGetLastError());
-    return 0;
-  };
+  const int grid = pl.n_items < nsm ? pl.n_items : nsm;
   int rc;
-  if (impl == NEMB200_SCORE_TC_LUT) rc = launch(k_score_tc<EPI_LUT>);
-  else if (impl == NEMB200_SCORE_TC_EX2) rc = launch(k_score_tc<EPI_EX2>);
-  else if (impl == NEMB200_SCORE_TC_EX2_2PASS) rc = launch(k_score_tc<EPI_EX2_2PASS>);
-  else { nemb200_set_error("unknown score impl %d", impl); return -1; }
+  static const char *mix_env = getenv("NEMB200_NO_MIX");  // diagnostics: pure table epilogue
+  const bool mix = mix_env == nullptr;
+  if (impl == NEMB200_SCORE_TC_LUT) {
+    switch (h->S) {
+      case 10: rc = launch_kernel(k_score_tc<EPI_LUT, 10, 10>, p, grid, st); break;
+      case 20: rc = mix ? launch_kernel(k_score_tc<EPI_LUT, 20, 12>, p, grid, st)
+                        : launch_kernel(k_score_tc<EPI_LUT, 20, 20>, p, grid, st); break;
+      case 30: rc = mix ? launch_kernel(k_score_tc<EPI_LUT, 30, 20>, p, grid, st)
+                        : launch_kernel(k_score_tc<EPI_LUT, 30, 30>, p, grid, st); break;
+      case 50: rc = mix ? launch_kernel(k_score_tc<EPI_LUT, 50, 32>, p, grid, st)
+                        : launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, st); break;
+      default: rc = launch_kernel(k_score_tc<EPI_LUT, 0, 0>, p, grid, st); break;
+    }
+  } else if (impl == NEMB200_SCORE_TC_EX2) {
+    rc = launch_kernel(k_score_tc<EPI_EX2, 0, 0>, p, grid, st);
+  } else if (impl == NEMB200_SCORE_TC_EX2_2PASS) {
+    rc = launch_kernel(k_score_tc<EPI_EX2_2PASS, 0, 0>, p, grid, st);
+  } else {
+    nemb200_set_error("unknown score impl %d", impl);
+    return -1;
+  }
   if (rc) return rc;
-  k_finalize<<<(n + 255) / 256, 256, 0, st>>>(p.partials, p.n_chunks, h->sumN, n, scores);
+  k_finalize<<<(n + 255) / 256, 256, 0, st>>>(p.partials, p.n_chunks * 2, h->sumN, n, scores);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
