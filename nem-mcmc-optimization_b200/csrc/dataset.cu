@@ -106,7 +106,8 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   NEMB_REQUIRE(h != nullptr, "out of host memory");
   uint8_t *base = (uint8_t *)d_workspace;
   h->S = S; h->E = E; h->W = L.W; h->KA = 1; h->n_mtiles = L.n_mtiles;
-  h->G = 256 / S < 16 ? 256 / S : 16;
+  h->G = 256 / S < 16 ? 256 / S : 16;          // graphs per MMA N tile: a multiple of 4 (one quarter per
+  h->G = h->G >= 4 ? (h->G & ~3) : 2;          // epilogue warpgroup), or 2 for S > 64
   h->A = A; h->B = B;
   h->alpha2 = -A * NEMB200_LOG2E; h->beta2 = B * NEMB200_LOG2E;
   h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_cnt = nullptr;

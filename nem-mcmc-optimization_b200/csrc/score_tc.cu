@@ -19,17 +19,20 @@
 // look-ups and MUFU ex2) so that neither is the single limiter.
 // No B x S x E intermediate ever reaches HBM: per (graph, E-chunk, warpgroup) one double is written.
 //
-// Roles (384 threads, no CTA-wide barrier in the main loop): warp 0 = TMA producer (A tiles, 4-stage
+// Roles (640 threads, no CTA-wide barrier in the main loop): warp 0 = TMA producer (A tiles, 4-stage
 // mbarrier ring), warp 1 = MMA issuer + TMEM owner (2 x 256-column accumulators), warps 2-3 = B-operand
-// expanders (double-buffered, run one work item ahead), warps 4-11 = two epilogue warpgroups that
-// alternate tiles.  Work items (N tile of graphs x chunk of E tiles) are statically strided over CTAs.
+// expanders (double-buffered, run one work item ahead), warps 4-19 = four epilogue warpgroups.  All four
+// drain the SAME accumulator buffer (each takes a quarter of the tile's graphs) while the MMA of the next
+// tile fills the other buffer, so the MMA + mbarrier hand-shake latency is hidden behind epilogue work and
+// four warps per scheduler hide the LDS / MUFU / TMEM latencies.  Work items (N tile of G graphs x chunk
+// of E tiles) are statically strided over CTAs.
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;
 constexpr int kStages = 4;
 constexpr int kTileBytes = 128 * 128;  // one operand atom: 128 rows x 128 B (SWIZZLE_128B)
 constexpr int kLutBytes = 64 * 256;
@@ -42,19 +45,22 @@ constexpr int OFF_B = OFF_LUT + kLutBytes;                  // 2 buffers x (256 
 constexpr int OFF_A = OFF_B + 2 * 2 * kTileBytes;           // kStages x 16 KB
 constexpr int OFF_BIAS = OFF_A + kStages * kTileBytes;      // 2 buffers x 1024 floats
 constexpr int OFF_ROWS = OFF_BIAS + 2 * 1024 * 4;           // 1024 words of bit rows (expander scratch)
-constexpr int OFF_RED = OFF_ROWS + 1024 * 4;                // 8 warps x 16 doubles
-constexpr int OFF_BAR = OFF_RED + 8 * kMaxG * 8;            // barriers + scalars
+constexpr int OFF_RED = OFF_ROWS + 1024 * 4;                // 16 warps x 8 doubles
+constexpr int OFF_BAR = OFF_RED + 16 * 8 * 8;               // barriers + scalars
 constexpr int kSmemBytes = OFF_BAR + 256;
 
 struct Params {
   const uint32_t *phi;   // [n_graphs][S][W]
   const uint8_t *a_img;  // [n_mtiles][16 KB]
   const float *lut;      // [64][64]
-  double *partials;      // [n_ntiles*G][n_chunks][2]
+  double *partials;      // [n_ntiles*G][n_chunks]
   int n_graphs, S, W, E, G, n_ntiles, n_mtiles, tpc, n_chunks, n_items, nmma, ksteps;
   float k1;              // EX2: x = k1 * acc + bias_j
   float kc;              // EX2: bias_j = kc * c_j - s
   float scale;           // s
+  long long *trace;      // diagnostics only: clock64 time line of CTA 0 (NULL normally)
+  int stagger;           // cycles by which warpgroups 2,3 trail warpgroups 0,1 at the start of an item
+  int debug;             // diagnostics only (NEMB200_DEBUG): 1 skip epilogue math, 2 skip MMA, 4 skip TMA, 8 skip expansion
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -72,6 +78,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
+}
+// non-blocking probe: the predicate can be consumed much later, hiding the ~150-cycle mbarrier latency
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -148,6 +166,12 @@ __device__ __forceinline__ float log2_split(float x) {
 
 enum { EPI_LUT = 0, EPI_EX2 = 1, EPI_EX2_2PASS = 2 };
 
+// diagnostics: time line slots [role 0..3][tile 0..255][event 0..3]
+#define TRACE(role, tile, ev)                                                                   \
+  do {                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && (tile) < 256) p.trace[((role) * 256 + (tile)) * 4 + (ev)] = clock64(); \
+  } while (0)
+
 // ---- generic epilogue (runtime S): one graph's columns [0, S) of one accumulator tile ---------------
 // Returns log2( 1 + sum_j 2^x_j ) for this thread's E-gene.
 template <int EPI, int CH>
@@ -185,61 +209,139 @@ __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *
 
 template <int EPI>
 __device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const float *sBias, const Params &p, bool valid,
-                                                      int ng, double (&part)[kMaxG]) {
-  const int S = p.S;
+                                                      int ng_mine, double (&part)[kMaxG / 4]) {
+  const int S = p.S, bstride = kBiasStride * (S > 64 ? 2 : 1);
 #pragma unroll
-  for (int g = 0; g < kMaxG; ++g) {
-    if (g < ng) {
-      float l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * S, S, sBias + g * kBiasStride * (S > 64 ? 2 : 1), p)
-                        : graph_lse2<EPI, 8>(taddr + g * S, S, sBias + g * kBiasStride, p);
+  for (int g = 0; g < kMaxG / 4; ++g) {
+    if (g < ng_mine) {
+      float l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * S, S, sBias + g * bstride, p)
+                        : graph_lse2<EPI, 8>(taddr + g * S, S, sBias + g * bstride, p);
       if (valid) part[g] += (double)l;
     }
   }
 }
 
-// ---- specialised epilogue (compile-time S): straight-line code over the whole tile ----------------------
-// Sites j < NLUT of every graph go through the shared-memory exp table (LSU pipe), the others through
-// I2F + FFMA + ex2.approx (ALU/FMA/MUFU pipes).  The next 32 accumulator columns are prefetched from TMEM
-// while the current 32 are consumed.
+// ---- specialised epilogue (compile-time S): straight-line code, software-pipelined over tiles ----------
+// A warpgroup owns NCOL = (G/4)*S_T accumulator columns of every tile, split in chunk A = the first 32
+// columns and chunk B = the rest.  Sites j < NLUT of every graph go through the shared-memory exp table
+// (LSU pipe), the others through I2F + FFMA + ex2.approx (ALU/FMA/MUFU pipes).  Per tile:
+//     [A(t) in registers]  issue TMEM load of B(t)  | math on A(t)
+//     [B(t) in registers]  release the accumulator buffer, wait for tile t+1, issue load of A(t+1) | math on B(t)
+// so every TMEM load and the MMA + mbarrier round trip of the next tile overlap this warp's own math.
+#define TMEM_LDN(n, taddr, r)                        \
+  do {                                               \
+    if ((n) > 16) TMEM_LD32(taddr, r);               \
+    else if ((n) > 8) TMEM_LD16(taddr, r);           \
+    else TMEM_LD8(taddr, r);                         \
+  } while (0)
+
+// Which attachment sites of a graph go through the exp table (true) and which through ex2.approx (false).
+// All warps of a CTA run in near lockstep, so the two kinds are interleaved in groups of four sites (a
+// float4 of biases) - otherwise the LSU and MUFU pipes would be used one after the other, not together.
+// NLUT == S_T: table only.  Otherwise every third group of four sites is an ex2 group.
 template <int S_T, int NLUT>
-__device__ __forceinline__ void tile_epilogue_static(uint32_t taddr, const float *sBias, const Params &p, bool valid,
-                                                     int ng, double (&part)[kMaxG]) {
-  constexpr int G = (256 / S_T) < kMaxG ? (256 / S_T) : kMaxG;
-  constexpr int NCOL = G * S_T;
-  constexpr int NCH = (NCOL + 31) / 32;
-  static_assert(NLUT % 4 == 0 || NLUT == S_T, "EX2 sites must start on a float4 boundary of the bias array");
-  uint32_t r[2][32];
+__host__ __device__ constexpr bool is_lut_site(int j) { return NLUT >= S_T ? true : ((j >> 2) % 3) != 2; }
+
+// The logarithm + float64 accumulation of a finished graph is deferred (pend_*) into the next graph's
+// look-up stream so that its MUFU / F2F / DADD latency chain is off the per-tile critical path.
+struct Pending { float sum; int g; bool valid; };
+__device__ __forceinline__ void finalize_pending(Pending &pd, const Params &p, double (&part)[kMaxG / 4]) {
+  if (pd.valid) {
+    const float l = log2_split(pd.sum) + p.scale;
+#pragma unroll
+    for (int g = 0; g < kMaxG / 4; ++g)
+      if (g == pd.g) part[g] += (double)l;
+  }
+  pd.valid = false;
+}
+
+template <int S_T, int NLUT, int C0, int C1>
+__device__ __forceinline__ void static_cols(const uint32_t (&r)[32], const float *sBias, const Params &p, bool valid,
+                                            int ng_mine, float (&acc)[4], float4 &b4, float null_term, Pending &pd,
+                                            double (&part)[kMaxG / 4]) {
+#pragma unroll
+  for (int col = C0; col < C1; ++col) {
+    const int g = col / S_T, j = col % S_T;
+    if (j == 0) { acc[0] = null_term; acc[1] = 0.f; acc[2] = 0.f; acc[3] = 0.f; }
+    float v;
+    if (is_lut_site<S_T, NLUT>(j)) {
+      v = lds_f32(r[col - C0]);
+    } else {
+      // (re)load the float4 of biases that holds site j (ex2 groups start on a 16-byte boundary)
+      if ((j & 3) == 0 || col == C0) b4 = *reinterpret_cast<const float4 *>(sBias + g * kBiasStride + (j & ~3));
+      const int w = j & 3;
+      const float b = w == 0 ? b4.x : (w == 1 ? b4.y : (w == 2 ? b4.z : b4.w));
+      v = ex2f(fmaf((float)(int)r[col - C0], p.k1, b));
+    }
+    if (j == 8 || (S_T <= 8 && j == S_T - 1)) finalize_pending(pd, p, part);  // previous graph, mid-stream
+    acc[j & 3] += v;
+    if (j == S_T - 1) {
+      if (S_T <= 8) finalize_pending(pd, p, part);
+      pd.sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      pd.g = g;
+      pd.valid = valid && g < ng_mine;
+    }
+  }
+}
+
+template <int S_T, int NLUT>
+__device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem_cols, const float *sBias, int ng_mine,
+                                                  int row0, int nt, uint32_t it0, uint32_t bar_tfull, uint32_t bar_tempty,
+                                                  double (&part)[kMaxG / 4]) {
+  constexpr int G = ((256 / S_T) < kMaxG ? (256 / S_T) : kMaxG) & ~3;
+  constexpr int NCOL = (G / 4) * S_T;  // this warpgroup's quarter of the tile's graphs
+  constexpr int NA = NCOL < 32 ? NCOL : 32, NB = NCOL - NA;
+  static_assert(NCOL <= 64, "a warpgroup's share must fit two 32-column TMEM loads");
+  const int lane = threadIdx.x & 31;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float null_term = ex2f(-p.scale);
-  TMEM_LD32(taddr, r[0]);
-  tmem_wait_ld();
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    if (ch + 1 < NCH) TMEM_LD32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int col = ch * 32 + i;
-      if (col < NCOL) {
-        const int g = col / S_T, j = col % S_T;
-        if (j == 0) { acc[0] = null_term; acc[1] = 0.f; acc[2] = 0.f; acc[3] = 0.f; }
-        float v;
-        if (j < NLUT) {
-          v = lds_f32(r[ch & 1][i]);
-        } else {
-          if (((j - NLUT) & 3) == 0) b4 = *reinterpret_cast<const float4 *>(sBias + g * kBiasStride + j);
-          const float b = ((j - NLUT) & 3) == 0 ? b4.x : (((j - NLUT) & 3) == 1 ? b4.y : (((j - NLUT) & 3) == 2 ? b4.z : b4.w));
-          v = ex2f(fmaf((float)(int)r[ch & 1][i], p.k1, b));
-        }
-        acc[j & 3] += v;
-        if (j == S_T - 1) {
-          const float l = log2_split((acc[0] + acc[1]) + (acc[2] + acc[3])) + p.scale;
-          if (valid && g < ng) part[g] += (double)l;
-        }
-      }
+  uint32_t ra[32], rb[32];
+  uint32_t buf = it0 & 1u;
+  mbar_wait(bar_tfull + 8 * buf, (it0 >> 1) & 1u);
+  tc_fence_after();
+  TMEM_LDN(NA, tmem_cols + buf * 256u, ra);
+#ifdef NEMB200_TRACE
+  const int trole = (threadIdx.x == 128) ? 0 : (threadIdx.x == 128 + 256 + 32 ? 1 : -1);
+#define ETRACE(ev)                                                                                     \
+  do {                                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && trole >= 0 && it0 + t < 256)                          \
+      p.trace[4096 + ((trole * 256 + (int)(it0 + t)) * 8) + (ev)] = clock64();                          \
+  } while (0)
+#else
+#define ETRACE(ev)
+#endif
+  Pending pd = {0.f, 0, false};
+  for (int t = 0; t < nt; ++t) {
+    const bool valid = row0 + t * 128 < p.E;
+    ETRACE(0);
+    tmem_wait_ld();  // A(t) is in registers
+    ETRACE(1);
+    if (NB > 0) TMEM_LDN(NB, tmem_cols + buf * 256u + 32u, rb);
+    static_cols<S_T, NLUT, 0, NA>(ra, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
+    ETRACE(2);
+    const uint32_t itn = it0 + (uint32_t)t + 1u, nbuf = itn & 1u;
+    uint32_t ready = 0;
+    if (t + 1 < nt) ready = mbar_test(bar_tfull + 8 * nbuf, (itn >> 1) & 1u);  // probe early, consume after the release
+    if (NB > 0) tmem_wait_ld();  // B(t) is in registers: this warp no longer needs the accumulator buffer
+    ETRACE(3);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    ETRACE(4);
+    if (t + 1 < nt) {
+      buf = nbuf;
+      if (!ready) mbar_wait(bar_tfull + 8 * buf, (itn >> 1) & 1u);
+      ETRACE(5);
+      tc_fence_after();
+      TMEM_LDN(NA, tmem_cols + buf * 256u, ra);
     }
-    if (ch + 1 < NCH) tmem_wait_ld();
+    ETRACE(6);
+    if (NB > 0) static_cols<S_T, NLUT, NA, NCOL>(rb, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
+    ETRACE(7);
   }
+  finalize_pending(pd, p, part);
+#undef ETRACE
 }
 
 template <int EPI, int S_T, int NLUT>
@@ -258,8 +360,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_aempty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4);
-      mbar_init(bar_bfull + 8 * i, 2); mbar_init(bar_edone + 8 * i, 8);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 16);
+      mbar_init(bar_bfull + 8 * i, 2); mbar_init(bar_edone + 8 * i, 16);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -289,6 +391,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
         for (int t = 0; t < nt; ++t, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1u;
           mbar_wait(bar_aempty + 8 * st, ph ^ 1u);
+          TRACE(0, it, 0);
+          if (p.debug & 4) { mbar_arrive(bar_afull + 8 * st); continue; }
           mbar_expect_tx(bar_afull + 8 * st, kTileBytes);
           bulk_g2s(sbase + OFF_A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, kTileBytes, bar_afull + 8 * st);
         }
@@ -307,14 +411,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
         const uint32_t b0 = sbase + OFF_B + bb * 2 * kTileBytes;
         for (int t = 0; t < nt; ++t, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1u, buf = it & 1u, bph = (it >> 1) & 1u;
+          TRACE(1, it, 0);
           mbar_wait(bar_afull + 8 * st, ph);
+          TRACE(1, it, 1);
           mbar_wait(bar_tempty + 8 * buf, bph ^ 1u);
+          TRACE(1, it, 2);
           tc_fence_after();
           const uint32_t a0 = sbase + OFF_A + st * kTileBytes;
-          for (int ks = 0; ks < p.ksteps; ++ks)
+          for (int ks = 0; ks < ((p.debug & 2) ? 0 : p.ksteps); ++ks)
             umma_i8(tmem_base + buf * 256u, umma_desc(a0 + ks * 32), umma_desc(b0 + ks * 32), idesc, ks > 0 ? 1u : 0u);
           umma_commit(bar_aempty + 8 * st);  // A slot reusable once these MMAs retire
           umma_commit(bar_tfull + 8 * buf);  // accumulator ready for the epilogue
+          TRACE(1, it, 3);
         }
       }
     }
@@ -329,11 +437,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
       if (k >= 2) mbar_wait(bar_edone + 8 * bb, ((k - 2) >> 1) & 1u);  // epilogue finished the item that used this buffer
       const int nwords = ng * S * W;
       for (int i = te; i < nwords; i += 64) sRows[i] = p.phi[(size_t)g0 * S * W + i];
-      asm volatile("bar.sync 3, 64;" ::: "memory");
+      asm volatile("bar.sync 5, 64;" ::: "memory");
       uint8_t *brow = smem + OFF_B + bb * 2 * kTileBytes;
       float *bias = reinterpret_cast<float *>(smem + OFF_BIAS) + bb * 1024;
       const int bstride = kBiasStride * (S > 64 ? 2 : 1);
-      for (int col = te; col < 256; col += 64) {
+      for (int col = te; col < ((p.debug & 8) ? 0 : 256); col += 64) {
         const int gi = col / S, j = col - gi * S;
         uint32_t anc[4] = {0u, 0u, 0u, 0u};
         int cnt = 0;
@@ -349,7 +457,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
         }
         // table look-up sites get the extra K row S: B = lut_base/128 (A holds 128 there), so that the
         // accumulator is the shared-memory address of lut[q][p]; unused columns point at lut[0][0]
-        const bool lut_site = EPI == EPI_LUT && gi < G && (S_T == 0 || j < NLUT);
+        bool lut_site = EPI == EPI_LUT && gi < G;
+        if constexpr (S_T > 0) lut_site = lut_site && is_lut_site<S_T, NLUT>(j);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t half = (anc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
@@ -370,55 +479,70 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_bfull + 8 * bb);
-      asm volatile("bar.sync 3, 64;" ::: "memory");  // sRows is reused by the next item
+      asm volatile("bar.sync 5, 64;" ::: "memory");  // sRows is reused by the next item
     }
   } else {
-    // =============================== epilogue: warpgroup wg handles tiles with (tile index & 1) == wg ======
+    // =============================== epilogue: 4 warpgroups share every tile, a quarter of its graphs each ===
     const int wg = (warp - 4) >> 2, quarter = warp & 3, tw = threadIdx.x - 128 - wg * 128;
+    const int gq = G >= 4 ? (G >> 2) : 1;                        // graphs per warpgroup (G == 2: warpgroups 2,3 idle)
+    const int bstride = kBiasStride * (S > 64 ? 2 : 1);
     uint32_t it = 0;
     for (int k = 0; k < n_my_items; ++k) {
       const int item = (int)blockIdx.x + k * (int)gridDim.x;
       const int chunk = item / p.n_ntiles, ntile = item % p.n_ntiles;
       const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
-      const int g0 = ntile * G, ng = min(G, p.n_graphs - g0);
+      const int gl = wg * gq;                                     // first graph (within the tile) of this warpgroup
+      const int g0 = ntile * G + gl;
+      const int ng_mine = gl < G ? max(0, min(gq, p.n_graphs - g0)) : 0;
       const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
-      const float *bias = reinterpret_cast<const float *>(smem + OFF_BIAS) + bb * 1024;
+      const float *bias = reinterpret_cast<const float *>(smem + OFF_BIAS) + bb * 1024 + gl * bstride;
       mbar_wait(bar_bfull + 8 * bb, bbph);  // bias values of this item are written
-      double part[kMaxG];
-#pragma unroll
-      for (int g = 0; g < kMaxG; ++g) part[g] = 0.0;
-      for (int t = 0; t < nt; ++t, ++it) {
-        const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
-        if ((int)buf != wg) continue;
-        mbar_wait(bar_tfull + 8 * buf, bph);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
-        const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
-        if constexpr (S_T > 0) tile_epilogue_static<S_T, NLUT>(taddr, bias, p, valid, ng, part);
-        else tile_epilogue_generic<EPI>(taddr, bias, p, valid, ng, part);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (p.stagger > 0 && wg >= 2) {  // de-synchronise the two halves of the epilogue warps
+        const long long t_start = clock64();
+        while (clock64() - t_start < p.stagger) {}
       }
-      // ---- per-item reduction inside the warpgroup -> one double per (graph, chunk, warpgroup)
+      double part[kMaxG / 4];
 #pragma unroll
-      for (int g = 0; g < kMaxG; ++g) {
-        if (g < ng) {
+      for (int g = 0; g < kMaxG / 4; ++g) part[g] = 0.0;
+      if (S_T > 0 && ng_mine > 0) {
+        if constexpr (S_T > 0)
+          item_tiles_static<S_T, NLUT>(p, tmem_base + (uint32_t)(gl * S) + ((uint32_t)(quarter * 32) << 16), bias, ng_mine,
+                                       m0 * 128 + quarter * 32 + lane, nt, it, bar_tfull, bar_tempty, part);
+        it += (uint32_t)nt;
+      } else {
+        for (int t = 0; t < nt; ++t, ++it) {
+          const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
+          mbar_wait(bar_tfull + 8 * buf, bph);
+          tc_fence_after();
+          if (ng_mine > 0 && !(p.debug & 1)) {
+            const uint32_t taddr = tmem_base + buf * 256u + (uint32_t)(gl * S) + ((uint32_t)(quarter * 32) << 16);
+            const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
+            tile_epilogue_generic<EPI>(taddr, bias, p, valid, ng_mine, part);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+      }
+      // ---- per-item reduction inside the warpgroup -> one double per (graph, chunk)
+#pragma unroll
+      for (int g = 0; g < kMaxG / 4; ++g) {
+        if (g < ng_mine) {
           double v = part[g];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) sRed[(warp - 4) * kMaxG + g] = v;
+          if (lane == 0) sRed[(warp - 4) * 8 + g] = v;
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_edone + 8 * bb);  // bias / B buffer of this item may be recycled
-      if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (tw < ng) {
+      asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+      if (tw < ng_mine) {
         double v = 0.0;
-        for (int w4 = 0; w4 < 4; ++w4) v += sRed[(wg * 4 + w4) * kMaxG + tw];
-        p.partials[((size_t)(g0 + tw) * p.n_chunks + chunk) * 2 + wg] = v;
+        for (int w4 = 0; w4 < 4; ++w4) v += sRed[(wg * 4 + w4) * 8 + tw];
+        p.partials[(size_t)(g0 + tw) * p.n_chunks + chunk] = v;
       }
-      if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
     }
   }
   tc_fence_before();
@@ -480,7 +604,7 @@ int launch_kernel(K kern, const Params &p, int grid, cudaStream_t st) {
 
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n) {
   Plan pl = make_plan(h, n, num_sms());
-  return 256 + sizeof(double) * 2 * (size_t)pl.n_ntiles * h->G * pl.n_chunks;
+  return 256 + sizeof(double) * (size_t)pl.n_ntiles * h->G * pl.n_chunks + 8 * 8192;  // + diagnostics time line
 }
 
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
@@ -508,8 +632,13 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   p.scale = impl == NEMB200_SCORE_TC_EX2_2PASS ? 0.f : (float)h->scale;
   const int grid = pl.n_items < nsm ? pl.n_items : nsm;
   int rc;
-  static const char *mix_env = getenv("NEMB200_NO_MIX");  // diagnostics: pure table epilogue
-  const bool mix = mix_env == nullptr;
+  static const char *dbg_env = getenv("NEMB200_DEBUG");
+  p.debug = dbg_env ? atoi(dbg_env) : 0;
+  p.trace = (p.debug & 32) ? reinterpret_cast<long long *>(reinterpret_cast<uint8_t *>(ws) + 256 + sizeof(double) * (size_t)pl.n_ntiles * h->G * pl.n_chunks) : nullptr;
+  static const char *stg_env = getenv("NEMB200_STAGGER");
+  p.stagger = stg_env ? atoi(stg_env) : 0;
+  static const char *mix_env = getenv("NEMB200_MIX");  // diagnostics: split sites between table and ex2.approx
+  const bool mix = mix_env != nullptr;
   if (impl == NEMB200_SCORE_TC_LUT) {
     switch (h->S) {
       case 10: rc = launch_kernel(k_score_tc<EPI_LUT, 10, 10>, p, grid, st); break;
@@ -530,7 +659,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
     return -1;
   }
   if (rc) return rc;
-  k_finalize<<<(n + 255) / 256, 256, 0, st>>>(p.partials, p.n_chunks * 2, h->sumN, n, scores);
+  k_finalize<<<(n + 255) / 256, 256, 0, st>>>(p.partials, p.n_chunks, h->sumN, n, scores);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
