@@ -93,11 +93,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_mcmc_propose(
   }
 }
 
-// counts[a*S+b] += k for every edge a->b of `bits`
+// counts[a*S+b] += k for every edge a->b of `bits`; eight independent read-modify-writes per lane are in
+// flight at a time so the warp is bandwidth- rather than latency-bound
 __device__ __forceinline__ void warp_add_edges(uint32_t *counts, const uint32_t *bits, int S, int W, uint32_t k, int lane) {
-  for (int cell = lane; cell < S * S; cell += 32) {
-    int a = cell / S, b = cell - a * S;
-    if ((bits[a * W + (b >> 5)] >> (b & 31)) & 1u) counts[cell] += k;
+  const int cells = S * S;
+  for (int base = 0; base < cells; base += 32 * 8) {
+    uint32_t v[8];
+    bool on[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int cell = base + u * 32 + lane;
+      on[u] = false;
+      if (cell < cells) {
+        const int a = cell / S, b = cell - a * S;
+        on[u] = (bits[a * W + (b >> 5)] >> (b & 31)) & 1u;
+      }
+      v[u] = on[u] ? counts[cell] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (on[u]) counts[base + u * 32 + lane] = v[u] + k;
   }
 }
 

@@ -117,13 +117,24 @@ class Dataset:
     """Device-resident observed knock-down matrix D (S x E, 0/1) + the error constants A, B (nem.py:17-18).
     Replaces the S x S x E score tables of the reference (nem.py:36-64)."""
 
-    def __init__(self, D, A: float, B: float, device=None):
+    def __init__(self, D, A: float, B: float, device=None, sort_egenes: bool = False):
+        """sort_egenes: store the E-genes (columns of D) sorted by knock-down pattern.  The score is a sum
+        over E-genes, so the order is free; similar neighbours make the 32 E-genes of a warp hit the same
+        exp-table entries (fewer shared-memory bank conflicts).  `self.egene_order[k]` is the original index
+        of stored column k (used to un-permute per-E-gene outputs)."""
         self.device = _require_cuda(device)
         L = _lib.lib()
         if isinstance(D, torch.Tensor):
-            d = (D != 0).to(torch.uint8).to(self.device).contiguous()
+            D = D.detach().cpu().numpy()
+        d_host = np.ascontiguousarray((np.asarray(D) != 0).astype(np.uint8))
+        if sort_egenes and d_host.shape[1] > 1:
+            # number of ones first (it bounds every count p), then the pattern itself
+            keys = [d_host[i] for i in range(d_host.shape[0] - 1, -1, -1)] + [d_host.sum(axis=0)]
+            self.egene_order = np.lexsort(keys)
+            d_host = np.ascontiguousarray(d_host[:, self.egene_order])
         else:
-            d = torch.from_numpy(np.ascontiguousarray((np.asarray(D) != 0).astype(np.uint8))).to(self.device)
+            self.egene_order = np.arange(d_host.shape[1])
+        d = torch.from_numpy(d_host).to(self.device)
         self.S, self.E = int(d.shape[0]), int(d.shape[1])
         self.A, self.B = float(A), float(B)
         nbytes = L.nemb200_dataset_bytes(self.S, self.E)
