@@ -228,7 +228,10 @@ def run_gpu(args, rank, world, local_rank):
     state = nb.ChainState(ds, orders0[lo:hi], 2.0 * S / E, edge_counts=True, chain_offset=lo, seed=1234,
                           rule=nb.RULE_MASKED, cand=cand, use_nem=True)
     state.run(max(Wm, 16))
-    mc_iters = max(K, 16) // 8 * 8
+    if world > 1:  # warm the collectives (NCCL communicator set-up is not part of a run)
+        parallel.allreduce_edge_counts(state.edge_count_matrix())
+        parallel.global_best(state.best_scores, state.best_orders, state.best_bits, lo)
+    mc_iters = max(2 * K, 64) // 8 * 8
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(torch.cuda.current_stream(dev))

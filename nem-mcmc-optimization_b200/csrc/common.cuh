@@ -26,6 +26,9 @@ struct nemb200_dataset {
   uint8_t *a_cnt;     // same shape, values {1,0}
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)
   double *sumN;       // [1] A * sum(D)   (nem.py:62 summed over e)
+  // one cached CUDA graph of the MCMC iteration body (re-used while the same buffers are passed)
+  unsigned long long mcmc_graph_key;
+  void *mcmc_graph_exec;  // cudaGraphExec_t
 };
 
 void nemb200_set_error(const char *fmt, ...);

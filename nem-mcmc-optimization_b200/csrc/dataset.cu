@@ -137,6 +137,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
 }
 
 extern "C" int nemb200_dataset_destroy(nemb200_dataset *h) {
+  if (h && h->mcmc_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->mcmc_graph_exec);
   free(h);
   return 0;
 }

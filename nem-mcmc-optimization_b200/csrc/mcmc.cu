@@ -325,28 +325,46 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
   constexpr int kUnroll = 8;
   int64_t done = 0;
   if (st != nullptr && n_iters >= 2 * kUnroll) {
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    NEMB_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = 0;
-    for (int u = 0; u < kUnroll && rc == 0; ++u) rc = step(0);
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc != 0 || ce != cudaSuccess) {
-      if (graph) cudaGraphDestroy(graph);
-      if (rc == 0) nemb200_set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
-      return rc ? rc : -2;
+    // the captured body depends only on these arguments (iteration indices live in device memory), so the
+    // instantiated graph is cached in the handle and re-used by later calls with the same buffers
+    unsigned long long key = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+    mix((unsigned long long)n); mix((unsigned long long)iter0 * 0 + 17); mix((unsigned long long)burn_in); mix((unsigned long long)(uintptr_t)d_gamma);
+    mix(sp); mix(seed); mix(chain_offset); mix((unsigned long long)rule); mix((unsigned long long)(uintptr_t)d_cand_bits);
+    mix((unsigned long long)use_nem); mix((unsigned long long)score_impl); mix((unsigned long long)(uintptr_t)d_orders);
+    mix((unsigned long long)(uintptr_t)d_curr_scores); mix((unsigned long long)(uintptr_t)d_curr_bits);
+    mix((unsigned long long)(uintptr_t)d_best_scores); mix((unsigned long long)(uintptr_t)d_best_orders);
+    mix((unsigned long long)(uintptr_t)d_best_bits); mix((unsigned long long)(uintptr_t)d_accept);
+    mix((unsigned long long)(uintptr_t)d_edge_counts); mix((unsigned long long)(uintptr_t)d_score_trace);
+    mix((unsigned long long)(uintptr_t)d_workspace); mix((unsigned long long)(uintptr_t)st);
+    mix((unsigned long long)iter0 * (d_score_trace != nullptr));  // the trace offset is baked into the kernels
+    nemb200_dataset *hm = const_cast<nemb200_dataset *>(h);
+    cudaGraphExec_t exec = (cudaGraphExec_t)hm->mcmc_graph_exec;
+    if (exec == nullptr || hm->mcmc_graph_key != key) {
+      if (exec) { cudaGraphExecDestroy(exec); hm->mcmc_graph_exec = nullptr; exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      NEMB_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int rc = 0;
+      for (int u = 0; u < kUnroll && rc == 0; ++u) rc = step(0);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc != 0 || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == 0) nemb200_set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+        return rc ? rc : -2;
+      }
+      cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) { nemb200_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); return -2; }
+      hm->mcmc_graph_exec = exec;
+      hm->mcmc_graph_key = key;
     }
-    NEMB_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     for (; done + kUnroll <= n_iters; done += kUnroll) {
       cudaError_t le = cudaGraphLaunch(exec, st);
       if (le != cudaSuccess) {
-        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
         nemb200_set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(le));
         return -2;
       }
     }
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
   }
   for (; done < n_iters; ++done) {
     int rc = step(0);
