@@ -36,7 +36,8 @@ enum {
   NEMB200_SCORE_WITNESS = 1, /* popcount + fp64 logsumexp CUDA kernel (independent witness) */
   NEMB200_SCORE_TC_LUT = 2,  /* tcgen05 GEMM + shared-memory exp-table epilogue */
   NEMB200_SCORE_TC_EX2 = 3,  /* tcgen05 GEMM + ex2 epilogue, fixed scale */
-  NEMB200_SCORE_TC_EX2_2PASS = 4 /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
+  NEMB200_SCORE_TC_EX2_2PASS = 4, /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
+  NEMB200_MCMC_FUSED = 5 /* nemb200_mcmc_run only: persistent one-CTA-per-chain kernel (small S*E) */
 };
 
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */
@@ -115,6 +116,8 @@ int nemb200_order_to_graph(const int32_t *d_orders, int n_chains, int S, int rul
  *        d_gamma       f64   [n]         per-chain inverse temperature (gamma of :224-229)
  *      iter0: global index of the first iteration (RNG counter / burn-in bookkeeping);
  *      resume == 0 scores the start orders first (method(), :258).
+ *      score_impl: NEMB200_SCORE_AUTO picks the persistent fused kernel for small problems (S*E <= 1e5,
+ *      n_chains <= 296) and the CUDA-graph loop around the tensor-core score otherwise.
  *      d_workspace: nemb200_mcmc_workspace_bytes(h, n_chains) bytes. */
 size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_chains);
 int nemb200_mcmc_run(const nemb200_dataset *h, int n_chains, int64_t n_iters, int64_t iter0,

@@ -9,7 +9,7 @@ import subprocess
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 _SO = os.path.join(_CSRC, "libnemb200.so")
-_SOURCES = ["dataset.cu", "graph.cu", "score_tc.cu", "mcmc.cu", "cell.cu"]
+_SOURCES = ["dataset.cu", "graph.cu", "score_tc.cu", "mcmc.cu", "mcmc_fused.cu", "cell.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

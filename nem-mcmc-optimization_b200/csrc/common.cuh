@@ -61,6 +61,14 @@ size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n);
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
                     int impl, cudaStream_t st);
 
+bool mcmc_fused_supported(const nemb200_dataset *h);
+bool mcmc_fused_preferred(const nemb200_dataset *h, int n_chains);
+int launch_mcmc_fused(const nemb200_dataset *h, int n, int64_t n_iters, int64_t iter0, int64_t burn_in, const double *d_gamma,
+                      unsigned long long sp, uint64_t seed, uint32_t chain_offset, int rule, const uint32_t *d_cand_bits,
+                      int use_nem, int resume, int32_t *d_orders, double *d_curr_scores, uint32_t *d_curr_bits,
+                      double *d_best_scores, int32_t *d_best_orders, uint32_t *d_best_bits, int64_t *d_accept,
+                      uint32_t *d_edge_counts, double *d_score_trace, cudaStream_t st);
+
 // ---- device helpers ------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -289,6 +289,10 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
   carve(h, n, d_workspace, &w);
   const int S = h->S, W = h->W;
   const unsigned long long sp = swap_prob >= 1.0 ? 0x100000000ull : (unsigned long long)(swap_prob * 4294967296.0 + 0.5);
+  if (score_impl == NEMB200_MCMC_FUSED || (score_impl == NEMB200_SCORE_AUTO && mcmc_fused_preferred(h, n)))
+    return launch_mcmc_fused(h, n, n_iters, iter0, burn_in, d_gamma, sp, seed, chain_offset, rule, d_cand_bits, use_nem,
+                             resume, d_orders, d_curr_scores, d_curr_bits, d_best_scores, d_best_orders, d_best_bits,
+                             d_accept, d_edge_counts, d_score_trace, st);
   const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock, thr = kWarpsPerBlock * 32;
 
   auto propose = [&](int init) -> int {

@@ -166,11 +166,20 @@ __device__ __forceinline__ float log2_split(float x) {
 
 enum { EPI_LUT = 0, EPI_EX2 = 1, EPI_EX2_2PASS = 2 };
 
-// diagnostics: time line slots [role 0..3][tile 0..255][event 0..3]
+// diagnostics (compile with -DNEMB200_TRACE): time line slots [role 0..3][tile 0..255][event 0..3]
+#ifdef NEMB200_TRACE
+#define DBG(flag) (p.debug & (flag))
+#else
+#define DBG(flag) false
+#endif
+#ifndef NEMB200_TRACE
+#define TRACE(role, tile, ev)
+#else
 #define TRACE(role, tile, ev)                                                                   \
   do {                                                                                           \
     if (p.trace != nullptr && blockIdx.x == 0 && (tile) < 256) p.trace[((role) * 256 + (tile)) * 4 + (ev)] = clock64(); \
   } while (0)
+#endif
 
 // ---- generic epilogue (runtime S): one graph's columns [0, S) of one accumulator tile ---------------
 // Returns log2( 1 + sum_j 2^x_j ) for this thread's E-gene.
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1u;
           mbar_wait(bar_aempty + 8 * st, ph ^ 1u);
           TRACE(0, it, 0);
-          if (p.debug & 4) { mbar_arrive(bar_afull + 8 * st); continue; }
+          if (DBG(4)) { mbar_arrive(bar_afull + 8 * st); continue; }
           mbar_expect_tx(bar_afull + 8 * st, kTileBytes);
           bulk_g2s(sbase + OFF_A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, kTileBytes, bar_afull + 8 * st);
         }
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
           TRACE(1, it, 2);
           tc_fence_after();
           const uint32_t a0 = sbase + OFF_A + st * kTileBytes;
-          for (int ks = 0; ks < ((p.debug & 2) ? 0 : p.ksteps); ++ks)
+          for (int ks = 0; ks < (DBG(2) ? 0 : p.ksteps); ++ks)
             umma_i8(tmem_base + buf * 256u, umma_desc(a0 + ks * 32), umma_desc(b0 + ks * 32), idesc, ks > 0 ? 1u : 0u);
           umma_commit(bar_aempty + 8 * st);  // A slot reusable once these MMAs retire
           umma_commit(bar_tfull + 8 * buf);  // accumulator ready for the epilogue
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
       uint8_t *brow = smem + OFF_B + bb * 2 * kTileBytes;
       float *bias = reinterpret_cast<float *>(smem + OFF_BIAS) + bb * 1024;
       const int bstride = kBiasStride * (S > 64 ? 2 : 1);
-      for (int col = te; col < ((p.debug & 8) ? 0 : 256); col += 64) {
+      for (int col = te; col < (DBG(8) ? 0 : 256); col += 64) {
         const int gi = col / S, j = col - gi * S;
         uint32_t anc[4] = {0u, 0u, 0u, 0u};
         int cnt = 0;
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
           const uint32_t buf = it & 1u, bph = (it >> 1) & 1u;
           mbar_wait(bar_tfull + 8 * buf, bph);
           tc_fence_after();
-          if (ng_mine > 0 && !(p.debug & 1)) {
+          if (ng_mine > 0 && !DBG(1)) {
             const uint32_t taddr = tmem_base + buf * 256u + (uint32_t)(gl * S) + ((uint32_t)(quarter * 32) << 16);
             const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
             tile_epilogue_generic<EPI>(taddr, bias, p, valid, ng_mine, part);

@@ -220,9 +220,10 @@ def _compare_chain(res, c, ref, S, tol=1e-6):
     assert res.curr_scores[c] == pytest.approx(ref["curr_score"], rel=tol)
 
 
+@pytest.mark.parametrize("impl", ["fused", "lut", "witness"])
 @pytest.mark.parametrize("S,E,rule,use_nem", [(10, 100, 0, True), (13, 126, 1, True), (13, 126, 1, False),
                                               (20, 300, 0, False), (40, 200, 1, True)])
-def test_mcmc_trajectory_vs_oracle(nb, S, E, rule, use_nem):
+def test_mcmc_trajectory_vs_oracle(nb, S, E, rule, use_nem, impl):
     """Same Philox draws as the oracle -> identical accept decisions, orders, best graphs and edge counts
     (a decision can only differ if |u - rate| is below the fp32-epilogue error; seeds are fixed)."""
     _, _, D = orc.synth_dataset(S, E, seed=7)
@@ -234,7 +235,7 @@ def test_mcmc_trajectory_vs_oracle(nb, S, E, rule, use_nem):
     orders0 = np.stack([rng.permutation(S) for _ in range(n_chains)]).astype(np.int32)
     ds = nb.Dataset(D, A, B)
     st = ds.run_chains(orders0, n_iter, gamma, swap_prob=0.9, seed=99, chain_offset=3, rule=rule, cand=cand,
-                       use_nem=use_nem, burn_in=burn, trace=True)
+                       use_nem=use_nem, burn_in=burn, trace=True, impl=impl)
     res = st.result()
     total = np.zeros((S, S), dtype=np.int64)
     for c in range(n_chains):
@@ -248,15 +249,16 @@ def test_mcmc_trajectory_vs_oracle(nb, S, E, rule, use_nem):
     assert 0 < res.accept_counts.sum() < n_chains * n_iter
 
 
-def test_mcmc_resume_equals_single_run(nb):
+@pytest.mark.parametrize("impl", ["fused", "lut"])
+def test_mcmc_resume_equals_single_run(nb, impl):
     S, E = 12, 150
     _, _, D = orc.synth_dataset(S, E, seed=2)
     A, B = orc.nem_constants(0.05, 0.1)
     ds = nb.Dataset(D, A, B)
     orders0 = np.stack([np.random.default_rng(c).permutation(S) for c in range(5)]).astype(np.int32)
-    a = ds.run_chains(orders0, 300, 0.2, seed=5, burn_in=100).result()
-    st = ds.run_chains(orders0, 120, 0.2, seed=5, burn_in=100)
-    st.run(37); st.run(143)
+    a = ds.run_chains(orders0, 300, 0.2, seed=5, burn_in=100, impl=impl).result()
+    st = ds.run_chains(orders0, 120, 0.2, seed=5, burn_in=100, impl=impl)
+    st.run(37, impl=impl); st.run(143, impl=impl)
     b = st.result()
     for f in ("best_scores", "best_orders", "curr_orders", "accept_counts", "edge_counts", "curr_scores"):
         assert np.array_equal(getattr(a, f), getattr(b, f)), f

@@ -5,6 +5,8 @@ import numpy as np, torch
 import nem_b200 as nb
 S, E, n = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (50, 10000, 1024)))
 _, _, D = nb.synth.dataset(S, E, seed=0)
+if os.environ.get('ZEROD'): D = D * 0
+if os.environ.get('RANDD'): D = (np.random.default_rng(0).random(D.shape) < 0.5).astype(np.uint8)
 ds = nb.Dataset(D, *nb.synth.nem_constants(0.05, 0.1), sort_egenes=os.environ.get('SORT','1')=='1')
 bits = ds.order_graphs(nb.synth.random_orders(n, S, 1), rule=1, cand=(np.random.default_rng(0).random((S, S)) < 0.3).astype(np.uint8))
 impl = sys.argv[4] if len(sys.argv) > 4 else "auto"
