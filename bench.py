@@ -106,6 +106,62 @@ def unclosed_graphs(n, seed):
     return ((pos[:, :, None] < pos[:, None, :]) & cand[None]).astype(np.uint8)
 
 
+def small_mcmc_configs(nb, synth, with_cpu):
+    """Order-MCMC iterations/s at BASELINE configs 1 and 2 (persistent fused kernel: one launch for the whole
+    run), next to the C oracle's loop on one host core."""
+    import torch
+    res = []
+    for name, s, e, n, iters in (("config 1: S=10 E=100 1 chain", 10, 100, 1, 10000), ("config 2: S=20 E=1000 64 chains", 20, 1000, 64, 4000)):
+        _, _, D = synth.dataset(s, e, seed=0, alpha=ALPHA, beta=BETA)
+        A, B = synth.nem_constants(ALPHA, BETA)
+        ds = nb.Dataset(D, A, B)
+        cand = (np.random.default_rng(0).random((s, s)) < 0.4).astype(np.uint8)
+        orders = synth.random_orders(n, s, 1)
+        st = nb.ChainState(ds, orders, 2.0 * s / e, seed=1234, rule=nb.RULE_MASKED, cand=cand, use_nem=True)
+        st.run(64)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(); st.run(iters); ev1.record(); torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        row = {"config": name, "value": n * iters / (ms * 1e-3), "unit": "chain-iterations/s", "iters": iters, "impl": "fused persistent kernel"}
+        if with_cpu:
+            from oracle import c_oracle
+            k = min(iters, 2000)
+            t0 = time.perf_counter()
+            c_oracle.mcmc_chain(D, A, B, orders[0], k, 2.0 * s / e, seed=1234, chain=0, rule=1, cand=cand, use_nem=True)
+            row["cpu_oracle_one_core_iters_per_s"] = k / (time.perf_counter() - t0)
+        res.append(row)
+    return res
+
+
+def config5_sweep(nb, synth):
+    """BASELINE config 5: 65 536 random DAGs, S=30 x E=5000: closure + score throughput, bit rows resident."""
+    import torch
+    s, e, n = 30, 5000, 65536
+    _, _, D = synth.dataset(s, e, seed=5, alpha=ALPHA, beta=BETA)
+    ds = nb.Dataset(D, *synth.nem_constants(ALPHA, BETA))
+    raw = torch.from_numpy(synth.random_dag_bits(n, s, seed=1).view(np.int32)).cuda()
+    closed = torch.empty_like(raw)
+    def sweep():
+        nb.closure(raw, S=s, return_bits=True)
+        return ds.score_bits(nb.closure(raw, S=s, return_bits=True))
+    for _ in range(2):
+        sweep()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    c = nb.closure(raw, S=s, return_bits=True)
+    ev[1].record()
+    ds.score_bits(c)
+    ev[2].record()
+    torch.cuda.synchronize()
+    t_c, t_s = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    hbm = peaks()[1]
+    return {"graphs": n, "closure_ms": t_c, "score_ms": t_s, "closures_per_s": n / (t_c * 1e-3), "graph_scores_per_s": n / (t_s * 1e-3),
+            "closure_hbm_frac": (2.0 * s * 4 * n / (t_c * 1e-3) / 1e9) / hbm if hbm else None,
+            "score_tflops_algorithmic": 2.0 * s * s * e * n / (t_s * 1e-3) / 1e12}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -279,6 +335,9 @@ def run_gpu(args, rank, world, local_rank):
                      "best_score": best[0], "edge_count_total": int(counts.sum().item())},
             "clocks": sampler.summary(),
         }
+        if world == 1:
+            out["mcmc_small"] = small_mcmc_configs(nb, synth, not args.no_cpu)
+            out["sweep_config5"] = config5_sweep(nb, synth)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             v0, _ = cpu_arm(D, A, B, unclosed_graphs(2 * cores, 2), cores)   # rate estimate

@@ -195,6 +195,46 @@ def test_score_full_size_c3_lut_vs_witness(nb):
         assert w[g] == pytest.approx(c_oracle.score(orc.order_to_graph(orders[g]), D, A, B), rel=REL_WITNESS)
 
 
+def test_score_config4_shape_vs_witness(nb):
+    """BASELINE config 4 shape (S=100, E=100 000): max-subtracted ex2 epilogue vs the fp64 witness on the device
+    and the C oracle for two graphs."""
+    S, E, n = 100, 100000, 48
+    rng = np.random.default_rng(4)
+    _, _, D = orc.synth_dataset(S, E, seed=4)
+    A, B = orc.nem_constants(0.05, 0.1)
+    ds = nb.Dataset(D, A, B)
+    assert not ds.lut_valid
+    cand = (rng.random((S, S)) < 0.2).astype(np.uint8)
+    orders = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
+    bits = ds.order_graphs(orders, rule=1, cand=cand, use_nem=True)
+    w = ds.score_bits(bits, impl="witness").cpu().numpy()
+    got = ds.score_bits(bits).cpu().numpy()
+    assert np.allclose(got, w, rtol=REL_TC), np.abs(got / w - 1).max()
+    graphs = nb.unpack_adj(bits[:2].cpu().numpy().view(np.uint32), S)
+    assert np.allclose(w[:2], c_oracle.score_batch(graphs, D, A, B, nthreads=2), rtol=REL_WITNESS)
+
+
+def test_score_config5_sweep(nb):
+    """BASELINE config 5: 65 536 random DAGs at S=30, E=5000 - closure + score of the whole batch; a slice is
+    checked against the witness, the oracle, and the batch result must not depend on batch composition."""
+    S, E, n = 30, 5000, 65536
+    _, _, D = orc.synth_dataset(S, E, seed=5)
+    A, B = orc.nem_constants(0.05, 0.1)
+    ds = nb.Dataset(D, A, B)
+    raw = nb.synth.random_dag_bits(n, S, seed=1)
+    dev = torch.from_numpy(raw.view(np.int32)).cuda()
+    closed = nb.closure(dev, S=S, return_bits=True)
+    scores = ds.score_bits(closed).cpu().numpy()
+    assert np.isfinite(scores).all()
+    sl = slice(1000, 1000 + 2048)
+    w = ds.score_bits(closed[sl].contiguous(), impl="witness").cpu().numpy()
+    assert np.allclose(scores[sl], w, rtol=REL_TC)
+    assert np.array_equal(ds.score_bits(closed[sl].contiguous()).cpu().numpy(), scores[sl])  # independent of the batch
+    g = nb.unpack_adj(raw[:3], S)
+    ref = [c_oracle.score(c_oracle.closure(x), D, A, B) for x in g]
+    assert np.allclose(scores[:3], ref, rtol=REL_TC)
+
+
 # ------------------------------------------------------------------------------------ order -> graph
 @pytest.mark.parametrize("S", [2, 10, 33, 50, 100])
 def test_order_to_graph_vs_oracle(nb, S):
