@@ -116,19 +116,22 @@ __device__ __forceinline__ void warp_add_edges(uint32_t *counts, const uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_mcmc_accept(
+constexpr int kAcceptThreads = 128;
+
+// one CTA per chain: every thread evaluates the (cheap) accept test, then the whole CTA applies it
+__global__ void __launch_bounds__(kAcceptThreads) k_mcmc_accept(
     int n, int S, int W, long long *iter_a, const long long *iter_b, long long iter0, long long burn_in, uint64_t seed,
     uint32_t chain_offset, const double *__restrict__ gamma, int init, const int32_t *__restrict__ prop_orders,
     const uint32_t *__restrict__ prop_bits, const double *__restrict__ prop_scores, int32_t *__restrict__ orders,
     double *__restrict__ curr_scores, uint32_t *__restrict__ curr_bits, double *__restrict__ best_scores,
     int32_t *__restrict__ best_orders, uint32_t *__restrict__ best_bits, long long *__restrict__ accept,
     uint32_t *__restrict__ edge_counts, long long *__restrict__ since, double *__restrict__ trace) {
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * kWarpsPerBlock + wib;
+  const int c = blockIdx.x, tid = threadIdx.x;
   const long long t = *iter_b;
-  if (!init && blockIdx.x == 0 && threadIdx.x == 0) *iter_a = t + 1;
-  if (c >= n) return;
+  if (!init && c == 0 && tid == 0) *iter_a = t + 1;
   const double ll = prop_scores[c];
+  const double curr = curr_scores[c], best = best_scores[c];
+  const long long since_c = since[c];
   bool acc, better;
   if (init) {
     acc = true; better = true;
@@ -136,37 +139,48 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_mcmc_accept(
     uint32_t ctr[4] = {(uint32_t)t, (uint32_t)((unsigned long long)t >> 32), chain_offset + (uint32_t)c, 0u};
     philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
     const double u = ((double)ctr[3] + 0.5) * (1.0 / 4294967296.0);
-    const double curr = curr_scores[c];
     acc = u < exp(gamma[c] * (ll - curr));            // accepting(), :224-229
-    better = acc && ll > best_scores[c];              // :290-292
-    if (trace != nullptr && lane == 0) {  // [iteration][0: proposed score, 1: current score after the decision][chain]
+    better = acc && ll > best;                        // :290-292
+    if (trace != nullptr && tid == 0) {  // [iteration][0: proposed score, 1: current score after the decision][chain]
       trace[((size_t)(t - iter0) * 2 + 0) * n + c] = ll;
       trace[((size_t)(t - iter0) * 2 + 1) * n + c] = acc ? ll : curr;
     }
   }
   if (!acc) return;
   const int nw = S * W;
+  __shared__ uint32_t old_bits[128 * 4];
   if (!init && edge_counts != nullptr) {
     // the graph being replaced was current for iterations [since, t-1]; count the post-burn-in ones
-    long long from = since[c] > burn_in ? since[c] : burn_in;
-    if (t > from) warp_add_edges(edge_counts + (size_t)c * S * S, curr_bits + (size_t)c * nw, S, W, (uint32_t)(t - from), lane);
-    __syncwarp();
-    if (lane == 0) since[c] = t;
+    const long long from = since_c > burn_in ? since_c : burn_in;
+    if (t > from) {
+      for (int i = tid; i < nw; i += kAcceptThreads) old_bits[i] = curr_bits[(size_t)c * nw + i];
+      __syncthreads();
+      const uint32_t k = (uint32_t)(t - from);
+      uint32_t *counts = edge_counts + (size_t)c * S * S;
+      for (int cell = tid; cell < S * S; cell += kAcceptThreads) {
+        const int a = cell / S, b = cell - a * S;
+        if ((old_bits[a * W + (b >> 5)] >> (b & 31)) & 1u) counts[cell] += k;
+      }
+    }
   }
-  for (int i = lane; i < S; i += 32) {
-    int v = prop_orders[(size_t)c * S + i];
+  __syncthreads();  // every thread has read curr/best/since of this chain before they are overwritten
+  for (int i = tid; i < S; i += kAcceptThreads) {
+    const int v = prop_orders[(size_t)c * S + i];
     orders[(size_t)c * S + i] = v;
     if (better) best_orders[(size_t)c * S + i] = v;
   }
-  for (int i = lane; i < nw; i += 32) {
-    uint32_t v = prop_bits[(size_t)c * nw + i];
+  for (int i = tid; i < nw; i += kAcceptThreads) {
+    const uint32_t v = prop_bits[(size_t)c * nw + i];
     curr_bits[(size_t)c * nw + i] = v;
     if (better) best_bits[(size_t)c * nw + i] = v;
   }
-  if (lane == 0) {
+  if (tid == 0) {
     curr_scores[c] = ll;
     if (better) best_scores[c] = ll;
-    if (!init) accept[c] += 1;
+    if (!init) {
+      accept[c] += 1;
+      if (edge_counts != nullptr) since[c] = t;
+    }
   }
 }
 
@@ -310,7 +324,7 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     if (rc) return rc;
     rc = score_dispatch(h, w.prop_bits, n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, st);
     if (rc) return rc;
-    k_mcmc_accept<<<grid, thr, 0, st>>>(n, S, W, w.iter_a, w.iter_b, iter0, burn_in, seed, chain_offset, d_gamma, init,
+    k_mcmc_accept<<<n, kAcceptThreads, 0, st>>>(n, S, W, w.iter_a, w.iter_b, iter0, burn_in, seed, chain_offset, d_gamma, init,
                                         w.prop_orders, w.prop_bits, w.prop_scores, d_orders, d_curr_scores, d_curr_bits,
                                         d_best_scores, d_best_orders, d_best_bits, (long long *)d_accept, d_edge_counts,
                                         w.since, d_score_trace);
