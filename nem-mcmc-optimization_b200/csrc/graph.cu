@@ -37,6 +37,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_closure(const uint32_t 
   }
 }
 
+// ---- closure, large batches of small graphs (S <= 32): one THREAD per graph -----------------------------
+// The whole S x S bit matrix of a graph lives in 32 registers of one thread, so the Warshall update is two
+// instructions per (i, k) pair with no shuffles; a CTA stages its 128 graphs through shared memory so that
+// global loads/stores stay coalesced (odd row stride: conflict-free).  ~3x fewer warp instructions per graph
+// than the warp-per-graph kernel; used when the batch is large enough to fill the machine (config 5).
+constexpr int kThreadClosureBlock = 128;
+__global__ void __launch_bounds__(kThreadClosureBlock) k_closure_thread(const uint32_t *__restrict__ adj, int n, int S,
+                                                                        uint32_t *__restrict__ out) {
+  __shared__ uint32_t sh[kThreadClosureBlock * 33];
+  const int g0 = blockIdx.x * kThreadClosureBlock, ng = min(kThreadClosureBlock, n - g0);
+  const int stride = S | 1;
+  const uint32_t *src = adj + (size_t)g0 * S;
+  for (int i = threadIdx.x; i < ng * S; i += kThreadClosureBlock) sh[(i / S) * stride + (i % S)] = src[i];
+  __syncthreads();
+  if ((int)threadIdx.x < ng) {
+    const uint32_t full = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = i < S ? (sh[threadIdx.x * stride + i] & full) : 0u;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < S) {
+        const uint32_t rk = r[k];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if ((r[i] >> k) & 1u) r[i] |= rk;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < S) sh[threadIdx.x * stride + i] = r[i];
+  }
+  __syncthreads();
+  uint32_t *dst = out + (size_t)g0 * S;
+  for (int i = threadIdx.x; i < ng * S; i += kThreadClosureBlock) dst[i] = sh[(i / S) * stride + (i % S)];
+}
+
 // ---- order -> graph: one warp per chain ----------------------------------------------------------
 // row(label at position p) = labels at positions > p  (get_permissible_parents :63-64 transposed to the
 // reference's dag orientation), optionally & candidate mask, optionally closed.
@@ -127,6 +164,11 @@ __global__ void k_witness_finalize(const double *part, int n_chunks, const doubl
 int launch_closure(const uint32_t *adj, int n, int S, uint32_t *out, cudaStream_t st) {
   if (n == 0) return 0;
   int W = (S + 31) / 32, grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (W == 1 && n >= 8192) {  // enough graphs to fill the machine with one thread per graph
+    k_closure_thread<<<(n + kThreadClosureBlock - 1) / kThreadClosureBlock, kThreadClosureBlock, 0, st>>>(adj, n, S, out);
+    NEMB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   switch (W) {
     case 1: k_closure<1><<<grid, kWarpsPerBlock * 32, 0, st>>>(adj, n, S, out); break;
     case 2: k_closure<2><<<grid, kWarpsPerBlock * 32, 0, st>>>(adj, n, S, out); break;

@@ -67,6 +67,28 @@ def test_closure_dense_and_empty(nb, golden):
     assert nb.closure(np.zeros((0, 10, 10), dtype=np.uint8), S=10).shape == (0, 10, 10)
 
 
+@pytest.mark.parametrize("S", [1, 2, 7, 16, 30, 31, 32])
+def test_closure_thread_per_graph_kernel(nb, S):
+    """Batches >= 8192 of graphs with S <= 32 take the one-thread-per-graph kernel: same bits as the oracle
+    (and as the warp-per-graph kernel used for smaller batches), in place as well."""
+    rng = np.random.default_rng(100 + S)
+    n = 8192 + 77
+    a = (rng.random((n, S, S)) < 0.08).astype(np.uint8)  # general digraphs, self loops and cycles included
+    bits = nb.pack_adj(a)
+    dev = torch.from_numpy(bits.view(np.int32)).cuda()
+    big = nb.closure(dev, S=S, return_bits=True)
+    small = torch.cat([nb.closure(dev[i:i + 2048].contiguous(), S=S, return_bits=True) for i in range(0, n, 2048)])
+    assert torch.equal(big, small)
+    got = nb.unpack_adj(big.cpu().numpy().view(np.uint32), S)
+    for g in rng.integers(0, n, 64):
+        assert np.array_equal(got[g], c_oracle.closure(a[g])), (S, g)
+    inplace = dev.clone()
+    import ctypes as C
+    nb._lib.check(nb._lib.lib().nemb200_closure_u32(C.c_void_p(inplace.data_ptr()), n, S, C.c_void_p(inplace.data_ptr()),
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(inplace, big)
+
+
 def test_closure_large_batch_properties(nb):
     """BASELINE config 5 size: 65536 random DAGs at S=30: idempotent, superset, acyclic-preserving."""
     rng = np.random.default_rng(5)
