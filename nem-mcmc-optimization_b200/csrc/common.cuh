@@ -14,6 +14,7 @@ struct nemb200_dataset {
   int S, E, W;        // S-genes, E-genes, words per bit row
   int KA;             // 64-element K atoms (bf16, SWIZZLE_128B rows of 128 B)
   int G;              // graphs per MMA N tile
+  int CS;             // accumulator columns per graph (S, or S rounded up to 8 for the specialised table kernels)
   int n_mtiles;       // E tiles of 128 rows
   double A, B;        // nem.py:17-18
   double alpha2, beta2;  // -A*log2(e), B*log2(e): log2-domain increments per ancestor with D=1 / D=0

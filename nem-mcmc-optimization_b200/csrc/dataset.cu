@@ -106,8 +106,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   NEMB_REQUIRE(h != nullptr, "out of host memory");
   uint8_t *base = (uint8_t *)d_workspace;
   h->S = S; h->E = E; h->W = L.W; h->KA = 1; h->n_mtiles = L.n_mtiles;
-  h->G = 256 / S < 16 ? 256 / S : 16;          // graphs per MMA N tile: a multiple of 4 (one quarter per
-  h->G = h->G >= 4 ? (h->G & ~3) : 2;          // epilogue warpgroup), or 2 for S > 64
+  h->CS = S;  // set below once the epilogue kind is known
   h->A = A; h->B = B;
   h->alpha2 = -A * NEMB200_LOG2E; h->beta2 = B * NEMB200_LOG2E;
   h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_cnt = nullptr;
@@ -121,6 +120,11 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   h->scale = (int)s;
   h->fixed_valid = s <= 100.0;
   h->lut_valid = h->fixed_valid && S <= 63;
+  // tile layout: the table kernels are compiled for a fixed number of accumulator columns per graph - S itself
+  // for the headline shapes, otherwise S rounded up to a multiple of 8 (padding sites read a zero table entry)
+  if (h->lut_valid && S >= 8 && !(S == 10 || S == 20 || S == 30 || S == 50)) h->CS = (S + 7) / 8 * 8;
+  h->G = 256 / h->CS < 16 ? 256 / h->CS : 16;   // graphs per MMA N tile: a multiple of 4 (one quarter per
+  h->G = h->G >= 4 ? (h->G & ~3) : 2;           // epilogue warpgroup), or 2 for S > 64
   int E_pad = L.n_mtiles * 128;
   k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
   k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, h->a_lut);

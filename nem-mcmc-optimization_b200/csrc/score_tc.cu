@@ -55,6 +55,7 @@ struct Params {
   const float *lut;      // [64][64]
   double *partials;      // [n_ntiles*G][n_chunks]
   int n_graphs, S, W, E, G, n_ntiles, n_mtiles, tpc, n_chunks, n_items, nmma, ksteps;
+  int CS;                // accumulator columns per graph (>= S; the specialised kernels pad S up to a multiple of 8)
   float k1;              // EX2: x = k1 * acc + bias_j
   float kc;              // EX2: bias_j = kc * c_j - s
   float scale;           // s
@@ -223,8 +224,8 @@ __device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const floa
 #pragma unroll
   for (int g = 0; g < kMaxG / 4; ++g) {
     if (g < ng_mine) {
-      float l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * S, S, sBias + g * bstride, p)
-                        : graph_lse2<EPI, 8>(taddr + g * S, S, sBias + g * bstride, p);
+      float l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * p.CS, S, sBias + g * bstride, p)
+                        : graph_lse2<EPI, 8>(taddr + g * p.CS, S, sBias + g * bstride, p);
       if (valid) part[g] += (double)l;
     }
   }
@@ -450,11 +451,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
       uint8_t *brow = smem + OFF_B + bb * 2 * kTileBytes;
       float *bias = reinterpret_cast<float *>(smem + OFF_BIAS) + bb * 1024;
       const int bstride = kBiasStride * (S > 64 ? 2 : 1);
+      const int CS = p.CS;
+      // padding sites (S <= j < CS) of the specialised kernels look up a table entry that is zero:
+      // offset 128*m with m odd is entry [q=(m-1)/2][p=32], zero as soon as 32 + (m-1)/2 > S
+      const uint32_t zero_m = S < 32 ? 1u : (uint32_t)(2 * (S - 32) + 3);
       for (int col = te; col < (DBG(8) ? 0 : 256); col += 64) {
-        const int gi = col / S, j = col - gi * S;
+        const int gi = col / CS, j = col - gi * CS;
         uint32_t anc[4] = {0u, 0u, 0u, 0u};
         int cnt = 0;
-        const bool used = gi < ng;
+        const bool used = gi < ng && j < S;
         if (used) {
           const uint32_t *rows = sRows + gi * S * W;
           const int jw = j >> 5, jb = j & 31;
@@ -477,13 +482,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
           v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
           v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
           if (lut_site && c == (S >> 4)) {
-            uint32_t ext = ((sbase + OFF_LUT) >> 7) << ((S & 3) * 8);
+            uint32_t extv = ((sbase + OFF_LUT) >> 7) + (j >= S ? zero_m : 0u);
+            if (extv > 255u) asm volatile("trap;");  // the table must sit in the first 32 KB of shared memory
+            uint32_t ext = extv << ((S & 3) * 8);
             int wsel = (S >> 2) & 3;
             if (wsel == 0) v.x |= ext; else if (wsel == 1) v.y |= ext; else if (wsel == 2) v.z |= ext; else v.w |= ext;
           }
           *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
         }
-        if (gi < G) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
+        if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
       for (int g = 0; g < kMaxG / 4; ++g) part[g] = 0.0;
       if (S_T > 0 && ng_mine > 0) {
         if constexpr (S_T > 0)
-          item_tiles_static<S_T, NLUT>(p, tmem_base + (uint32_t)(gl * S) + ((uint32_t)(quarter * 32) << 16), bias, ng_mine,
+          item_tiles_static<S_T, NLUT>(p, tmem_base + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16), bias, ng_mine,
                                        m0 * 128 + quarter * 32 + lane, nt, it, bar_tfull, bar_tempty, part);
         it += (uint32_t)nt;
       } else {
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
           mbar_wait(bar_tfull + 8 * buf, bph);
           tc_fence_after();
           if (ng_mine > 0 && !DBG(1)) {
-            const uint32_t taddr = tmem_base + buf * 256u + (uint32_t)(gl * S) + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t taddr = tmem_base + buf * 256u + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16);
             const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
             tile_epilogue_generic<EPI>(taddr, bias, p, valid, ng_mine, part);
           }
@@ -632,7 +639,8 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   p.partials = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(ws) + 256);
   p.n_graphs = n; p.S = h->S; p.W = h->W; p.E = h->E; p.G = h->G;
   p.n_ntiles = pl.n_ntiles; p.n_mtiles = h->n_mtiles; p.tpc = pl.tpc; p.n_chunks = pl.n_chunks; p.n_items = pl.n_items;
-  p.nmma = (h->G * h->S + 15) / 16 * 16;
+  p.CS = h->CS;
+  p.nmma = (h->G * h->CS + 15) / 16 * 16;
   p.ksteps = (h->S + (impl == NEMB200_SCORE_TC_LUT ? 1 : 0) + 31) / 32;
   // accumulator a = 4p + 256q = 256c - 252p  ->  x = alpha2*p + beta2*q = k1*a + kc*c
   const double kappa2 = h->alpha2 - h->beta2;
@@ -644,19 +652,22 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   static const char *dbg_env = getenv("NEMB200_DEBUG");
   p.debug = dbg_env ? atoi(dbg_env) : 0;
   p.trace = (p.debug & 32) ? reinterpret_cast<long long *>(reinterpret_cast<uint8_t *>(ws) + 256 + sizeof(double) * (size_t)pl.n_ntiles * h->G * pl.n_chunks) : nullptr;
-  static const char *stg_env = getenv("NEMB200_STAGGER");
-  p.stagger = stg_env ? atoi(stg_env) : 0;
-  static const char *mix_env = getenv("NEMB200_MIX");  // diagnostics: split sites between table and ex2.approx
-  const bool mix = mix_env != nullptr;
+  p.stagger = 0;
   if (impl == NEMB200_SCORE_TC_LUT) {
-    switch (h->S) {
+    // the dataset fixed the column stride: S itself for the four headline shapes, S rounded up to 8 otherwise
+    switch (h->CS == h->S ? h->S : -h->CS) {
       case 10: rc = launch_kernel(k_score_tc<EPI_LUT, 10, 10>, p, grid, st); break;
-      case 20: rc = mix ? launch_kernel(k_score_tc<EPI_LUT, 20, 12>, p, grid, st)
-                        : launch_kernel(k_score_tc<EPI_LUT, 20, 20>, p, grid, st); break;
-      case 30: rc = mix ? launch_kernel(k_score_tc<EPI_LUT, 30, 20>, p, grid, st)
-                        : launch_kernel(k_score_tc<EPI_LUT, 30, 30>, p, grid, st); break;
-      case 50: rc = mix ? launch_kernel(k_score_tc<EPI_LUT, 50, 32>, p, grid, st)
-                        : launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, st); break;
+      case 20: rc = launch_kernel(k_score_tc<EPI_LUT, 20, 20>, p, grid, st); break;
+      case 30: rc = launch_kernel(k_score_tc<EPI_LUT, 30, 30>, p, grid, st); break;
+      case 50: rc = launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, st); break;
+      case 8: case -8: rc = launch_kernel(k_score_tc<EPI_LUT, 8, 8>, p, grid, st); break;
+      case 16: case -16: rc = launch_kernel(k_score_tc<EPI_LUT, 16, 16>, p, grid, st); break;
+      case 24: case -24: rc = launch_kernel(k_score_tc<EPI_LUT, 24, 24>, p, grid, st); break;
+      case 32: case -32: rc = launch_kernel(k_score_tc<EPI_LUT, 32, 32>, p, grid, st); break;
+      case 40: case -40: rc = launch_kernel(k_score_tc<EPI_LUT, 40, 40>, p, grid, st); break;
+      case 48: case -48: rc = launch_kernel(k_score_tc<EPI_LUT, 48, 48>, p, grid, st); break;
+      case 56: case -56: rc = launch_kernel(k_score_tc<EPI_LUT, 56, 56>, p, grid, st); break;
+      case -64: rc = launch_kernel(k_score_tc<EPI_LUT, 64, 64>, p, grid, st); break;
       default: rc = launch_kernel(k_score_tc<EPI_LUT, 0, 0>, p, grid, st); break;
     }
   } else if (impl == NEMB200_SCORE_TC_EX2) {
