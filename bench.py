@@ -130,6 +130,12 @@ def small_mcmc_configs(nb, synth, with_cpu):
             t0 = time.perf_counter()
             c_oracle.mcmc_chain(D, A, B, orders[0], k, 2.0 * s / e, seed=1234, chain=0, rule=1, cand=cand, use_nem=True)
             row["cpu_oracle_one_core_iters_per_s"] = k / (time.perf_counter() - t0)
+            # the numpy restatement of the reference loop (closest to the reference's own numpy path)
+            from oracle import nem_oracle as orc
+            k2 = 300 if s <= 10 else 60
+            t0 = time.perf_counter()
+            orc.mcmc_chain(D, A, B, orders[0], k2, 2.0 * s / e, seed=1234, chain=0, rule=1, cand=cand, use_nem=True)
+            row["cpu_numpy_port_one_core_iters_per_s"] = k2 / (time.perf_counter() - t0)
         res.append(row)
     return res
 

@@ -139,6 +139,15 @@ int nemb200_replica_exchange(int n_chains, int ladder, int phase, int64_t round,
                              double *d_curr_scores, uint32_t *d_curr_bits, int64_t *d_n_swaps,
                              void *stream);
 
+/* ---- device-side data synthesis: replaces utils.create_real_knockdown_mat (utils.py:15-23) and
+ *      utils.create_observed_knockdown_mat (utils.py:25-35) for large shapes.  d_adj_bits: the (closed) true
+ *      graph as S x W bit rows; d_end_nodes: int32 [E] attachment of every E-gene; d_real (may be NULL) and
+ *      d_observed: S x E row-major uint8 out.  The flip uniform of cell i*E+e is Philox4x32-10(key = seed,
+ *      counter = (cell lo, cell hi, 0, 2)) word 0 (the reference uses MT19937, so only the law is the same). */
+int nemb200_synth_knockdown(const uint32_t *d_adj_bits, const int32_t *d_end_nodes, int S, int E,
+                            double alpha, double beta, uint64_t seed, uint8_t *d_real,
+                            uint8_t *d_observed, void *stream);
+
 /* ---- posterior edge frequencies: sum per-chain counts into int64 [S*S] (what the NCCL
  *      all-reduce then sums across GPUs).  New in this build. */
 int nemb200_edge_counts_reduce(const uint32_t *d_edge_counts, int n_chains, int S,

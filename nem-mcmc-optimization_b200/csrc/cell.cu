@@ -92,3 +92,39 @@ extern "C" int nemb200_cell_ll(const double *d_cell, int rows, int E, double *d_
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- device-side data synthesis: utils.create_real_knockdown_mat (utils.py:15-23) and
+//      utils.create_observed_knockdown_mat (utils.py:25-35) for shapes where the reference's Python double
+//      loop (S*E calls of random.random()) takes minutes.  The flip uniform of cell (i, e) is Philox4x32-10 with
+//      key = seed and counter = (cell lo, cell hi, 0, 2), cell = i*E + e, u = (word0 + 0.5) / 2^32.
+namespace {
+__global__ void k_synth_knockdown(const uint32_t *__restrict__ adj_bits, const int32_t *__restrict__ end_nodes, int S, int W,
+                                  int E, double alpha, double beta, uint64_t seed, uint8_t *__restrict__ real,
+                                  uint8_t *__restrict__ obs) {
+  const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= (size_t)S * E) return;
+  const int i = (int)(cell / E), e = (int)(cell - (size_t)i * E);
+  const int k = end_nodes[e];
+  // E-gene e hangs on S-gene k: it reacts to the knock-down of k and of every i with an edge i -> k (utils.py:5-23)
+  const int r = (i == k) || ((adj_bits[i * W + (k >> 5)] >> (k & 31)) & 1u);
+  uint32_t ctr[4] = {(uint32_t)cell, (uint32_t)((unsigned long long)cell >> 32), 0u, 2u};
+  philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u = ((double)ctr[0] + 0.5) * (1.0 / 4294967296.0);
+  int o = r;
+  if (r == 0 && u < alpha) o = 1;        // false positive, utils.py:31-32
+  else if (r == 1 && u < beta) o = 0;    // false negative, utils.py:33-34
+  if (real != nullptr) real[cell] = (uint8_t)r;
+  obs[cell] = (uint8_t)o;
+}
+}  // namespace
+
+extern "C" int nemb200_synth_knockdown(const uint32_t *d_adj_bits, const int32_t *d_end_nodes, int S, int E, double alpha,
+                                       double beta, uint64_t seed, uint8_t *d_real, uint8_t *d_observed, void *stream) {
+  NEMB_REQUIRE(d_adj_bits && d_end_nodes && d_observed, "null argument");
+  NEMB_REQUIRE(S >= 1 && S <= NEMB200_MAX_S && E >= 1, "bad shape S=%d E=%d", S, E);
+  const size_t cells = (size_t)S * E;
+  k_synth_knockdown<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_adj_bits, d_end_nodes, S, (S + 31) / 32, E,
+                                                                                     alpha, beta, seed, d_real, d_observed);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -124,17 +124,21 @@ class Dataset:
         of stored column k (used to un-permute per-E-gene outputs)."""
         self.device = _require_cuda(device)
         L = _lib.lib()
-        if isinstance(D, torch.Tensor):
-            D = D.detach().cpu().numpy()
-        d_host = np.ascontiguousarray((np.asarray(D) != 0).astype(np.uint8))
-        if sort_egenes and d_host.shape[1] > 1:
-            # number of ones first (it bounds every count p), then the pattern itself
-            keys = [d_host[i] for i in range(d_host.shape[0] - 1, -1, -1)] + [d_host.sum(axis=0)]
-            self.egene_order = np.lexsort(keys)
-            d_host = np.ascontiguousarray(d_host[:, self.egene_order])
+        if isinstance(D, torch.Tensor) and D.is_cuda and not sort_egenes:
+            d = (D != 0).to(torch.uint8).to(self.device).contiguous()  # already on the device (e.g. synth.device_knockdown)
+            self.egene_order = np.arange(d.shape[1])
         else:
-            self.egene_order = np.arange(d_host.shape[1])
-        d = torch.from_numpy(d_host).to(self.device)
+            if isinstance(D, torch.Tensor):
+                D = D.detach().cpu().numpy()
+            d_host = np.ascontiguousarray((np.asarray(D) != 0).astype(np.uint8))
+            if sort_egenes and d_host.shape[1] > 1:
+                # number of ones first (it bounds every count p), then the pattern itself
+                keys = [d_host[i] for i in range(d_host.shape[0] - 1, -1, -1)] + [d_host.sum(axis=0)]
+                self.egene_order = np.lexsort(keys)
+                d_host = np.ascontiguousarray(d_host[:, self.egene_order])
+            else:
+                self.egene_order = np.arange(d_host.shape[1])
+            d = torch.from_numpy(d_host).to(self.device)
         self.S, self.E = int(d.shape[0]), int(d.shape[1])
         self.A, self.B = float(A), float(B)
         nbytes = L.nemb200_dataset_bytes(self.S, self.E)

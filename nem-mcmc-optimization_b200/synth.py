@@ -76,3 +76,24 @@ def random_dag_bits(n: int, S: int, seed: int = 0, percent: int = 40) -> np.ndar
         a = (rng.integers(0, 101, size=(m, S, S)) < percent) & allowed[None]
         out[lo:lo + m] = pack_adj(a.astype(np.uint8))
     return out
+
+
+def device_knockdown(adj, end_nodes, alpha: float = 0.05, beta: float = 0.1, seed: int = 0, device=None, want_real=False):
+    """Real and observed knock-down matrices generated on the GPU (nemb200_synth_knockdown): the data model of
+    utils.py:15-35 with Philox flips.  adj: (S,S) closed true graph; end_nodes: (E,) attachments.
+    Returns the observed matrix as a uint8 CUDA tensor (S,E) (and the noise-free one if want_real)."""
+    import ctypes as C
+    import torch
+    from . import _lib, engine
+    dev = engine._require_cuda(device)
+    adj = np.asarray(adj)
+    S, E = adj.shape[0], len(end_nodes)
+    bits = torch.from_numpy(engine.pack_adj(adj).view(np.int32)).to(dev)
+    ends = torch.from_numpy(np.ascontiguousarray(np.asarray(end_nodes, dtype=np.int32))).to(dev)
+    obs = torch.empty((S, E), dtype=torch.uint8, device=dev)
+    real = torch.empty((S, E), dtype=torch.uint8, device=dev) if want_real else None
+    st = torch.cuda.current_stream(dev)
+    _lib.check(_lib.lib().nemb200_synth_knockdown(engine._ptr(bits), engine._ptr(ends), S, E, float(alpha), float(beta),
+                                                 C.c_uint64(int(seed)), engine._ptr(real), engine._ptr(obs),
+                                                 engine._stream_ptr(st)))
+    return (obs, real) if want_real else obs

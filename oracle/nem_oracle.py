@@ -358,3 +358,22 @@ def synth_dataset(S, E, seed=0, alpha=0.05, beta=0.1):
     D[(real == 0) & (u < alpha)] = 1
     D[(real == 1) & (u < beta)] = 0
     return adj, end_nodes, D.astype(np.uint8)
+
+
+def philox_observed(adj, end_nodes, alpha, beta, seed):
+    """Restatement of utils.create_real_knockdown_mat + create_observed_knockdown_mat (utils.py:15-35) with the
+    Philox flip stream of nemb200_synth_knockdown: cell i*E+e uses counter (cell lo, cell hi, 0, 2), word 0."""
+    real = create_real_knockdown_mat(adj, end_nodes).astype(np.uint8)
+    S, E = real.shape
+    k0, k1 = seed & _M32, (seed >> 32) & _M32
+    obs = real.copy()
+    for i in range(S):
+        for e in range(E):
+            cell = i * E + e
+            r0 = philox4x32_10(cell & _M32, (cell >> 32) & _M32, 0, 2, k0, k1)[0]
+            u = (r0 + 0.5) / 4294967296.0
+            if real[i, e] == 0 and u < alpha:
+                obs[i, e] = 1
+            elif real[i, e] == 1 and u < beta:
+                obs[i, e] = 0
+    return real, obs

@@ -438,3 +438,26 @@ def test_mcmc_cell_ratio_methods(nb, golden):
         ow, ll = mc.calculate_ll()
         assert ll == pytest.approx(float(np.logaddexp.reduce(ref, axis=0).sum()), rel=1e-12)
     assert nb.utils.compute_ll(ref) == pytest.approx(ll, rel=1e-12)
+
+
+def test_device_synthesis_vs_oracle(nb):
+    """nemb200_synth_knockdown is bit-exact against the oracle restatement of utils.py:15-35 driven
+    by the same Philox stream, and has the flip rates alpha / beta at a large shape."""
+    rng = np.random.default_rng(8)
+    S, E = 13, 300
+    adj = c_oracle.closure(nb.synth.random_dag(S, rng))
+    ends = rng.integers(0, S, E)
+    obs, real = nb.synth.device_knockdown(adj, ends, 0.05, 0.1, seed=77, want_real=True)
+    r_ref, o_ref = orc.philox_observed(adj, ends, 0.05, 0.1, 77)
+    assert np.array_equal(real.cpu().numpy(), r_ref) and np.array_equal(obs.cpu().numpy(), o_ref)
+    S, E = 100, 100000
+    adj = c_oracle.closure(nb.synth.random_dag(S, rng))
+    ends = rng.integers(0, S, E)
+    obs, real = nb.synth.device_knockdown(adj, ends, 0.05, 0.1, seed=5, want_real=True)
+    assert np.array_equal(real.cpu().numpy(), orc.create_real_knockdown_mat(adj, ends).astype(np.uint8))
+    r, o = real.bool(), obs.bool()
+    fp = (o & ~r).sum().item() / max(1, (~r).sum().item())
+    fn = (~o & r).sum().item() / max(1, r.sum().item())
+    assert abs(fp - 0.05) < 0.002 and abs(fn - 0.1) < 0.004
+    ds = nb.Dataset(obs, *orc.nem_constants(0.05, 0.1))   # device tensor accepted as data
+    assert np.isfinite(ds.score_graphs(adj[None].astype(np.uint8))[0])
