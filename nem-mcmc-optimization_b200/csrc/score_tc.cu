@@ -60,7 +60,6 @@ struct Params {
   float kc;              // EX2: bias_j = kc * c_j - s
   float scale;           // s
   long long *trace;      // diagnostics only: clock64 time line of CTA 0 (NULL normally)
-  int stagger;           // cycles by which warpgroups 2,3 trail warpgroups 0,1 at the start of an item
   int debug;             // diagnostics only (NEMB200_DEBUG): 1 skip epilogue math, 2 skip MMA, 4 skip TMA, 8 skip expansion
 };
 
@@ -513,10 +512,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
       const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
       const float *bias = reinterpret_cast<const float *>(smem + OFF_BIAS) + bb * 1024 + gl * bstride;
       mbar_wait(bar_bfull + 8 * bb, bbph);  // bias values of this item are written
-      if (p.stagger > 0 && wg >= 2) {  // de-synchronise the two halves of the epilogue warps
-        const long long t_start = clock64();
-        while (clock64() - t_start < p.stagger) {}
-      }
       double part[kMaxG / 4];
 #pragma unroll
       for (int g = 0; g < kMaxG / 4; ++g) part[g] = 0.0;
@@ -652,7 +647,6 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   static const char *dbg_env = getenv("NEMB200_DEBUG");
   p.debug = dbg_env ? atoi(dbg_env) : 0;
   p.trace = (p.debug & 32) ? reinterpret_cast<long long *>(reinterpret_cast<uint8_t *>(ws) + 256 + sizeof(double) * (size_t)pl.n_ntiles * h->G * pl.n_chunks) : nullptr;
-  p.stagger = 0;
   if (impl == NEMB200_SCORE_TC_LUT) {
     // the dataset fixed the column stride: S itself for the four headline shapes, S rounded up to 8 otherwise
     switch (h->CS == h->S ? h->S : -h->CS) {

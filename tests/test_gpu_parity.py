@@ -461,3 +461,70 @@ def test_device_synthesis_vs_oracle(nb):
     assert abs(fp - 0.05) < 0.002 and abs(fn - 0.1) < 0.004
     ds = nb.Dataset(obs, *orc.nem_constants(0.05, 0.1))   # device tensor accepted as data
     assert np.isfinite(ds.score_graphs(adj[None].astype(np.uint8))[0])
+
+
+def test_c_abi_error_paths(nb):
+    """Status codes + nemb200_last_error for bad arguments (nothing is launched)."""
+    import ctypes as C
+    L = nb._lib.lib()
+    S, E = 20, 100
+    D = (np.random.default_rng(0).random((S, E)) < 0.5).astype(np.uint8)
+    ds = nb.Dataset(D, *orc.nem_constants(0.05, 0.1))
+    bits = ds.order_graphs(np.arange(S)[None])
+    out = torch.empty(1, dtype=torch.float64, device="cuda")
+    ws = torch.empty(16, dtype=torch.uint8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = L.nemb200_score_batch(ds._h, C.c_void_p(bits.data_ptr()), 1, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), 16, 0, st)
+    assert rc < 0 and b"workspace" in L.nemb200_last_error()
+    rc = L.nemb200_score_batch(ds._h, None, 1, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), 16, 0, st)
+    assert rc < 0 and b"null" in L.nemb200_last_error()
+    rc = L.nemb200_closure_u32(C.c_void_p(bits.data_ptr()), 1, 129, C.c_void_p(bits.data_ptr()), st)
+    assert rc < 0 and b"S must be" in L.nemb200_last_error()
+    rc = L.nemb200_order_to_graph(C.c_void_p(bits.data_ptr()), 1, S, 1, None, 1, C.c_void_p(bits.data_ptr()), st)
+    assert rc < 0 and b"candidate" in L.nemb200_last_error()
+    with pytest.raises(nb._lib.NemB200Error):
+        ds.score_graphs(np.zeros((1, S, S), dtype=np.uint8), impl=17)
+    with pytest.raises(ValueError):
+        ds.score_graphs(np.zeros((1, S + 1, S + 1), dtype=np.uint8))
+    with pytest.raises(ValueError):
+        ds.run_chains(np.zeros((2, S), dtype=np.int32), 1, 0.1)   # not permutations
+
+
+def test_sorted_egenes_and_multichain_loop_path(nb):
+    """Dataset(sort_egenes=True) is score-invariant; > 296 chains take the CUDA-graph loop even for a small
+    problem and agree with the persistent kernel chain by chain (same global chain ids)."""
+    S, E = 16, 500
+    _, _, D = orc.synth_dataset(S, E, seed=9)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rng = np.random.default_rng(2)
+    graphs = rand_dags(rng, 33, S)
+    a = nb.Dataset(D, A, B).score_graphs(graphs)
+    b = nb.Dataset(D, A, B, sort_egenes=True).score_graphs(graphs)
+    assert np.allclose(a, b, rtol=1e-12)
+    n = 320
+    orders0 = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
+    ds = nb.Dataset(D, A, B)
+    loop = ds.run_chains(orders0, 64, 0.1, seed=3).result()            # auto -> loop (n > 296)
+    fused = ds.run_chains(orders0[:64], 64, 0.1, seed=3).result()       # auto -> persistent kernel
+    assert np.array_equal(loop.curr_orders[:64], fused.curr_orders)
+    assert np.array_equal(loop.accept_counts[:64], fused.accept_counts)
+    assert np.allclose(loop.best_scores[:64], fused.best_scores, rtol=1e-12)
+
+
+def test_replica_exchange_swap_rate(nb):
+    """Swap decisions follow u < exp(-delta) (nem_order_mcmc.py:333-337): with equal gammas delta = 0, so every
+    pair swaps; with a wide ladder and spread-out scores fewer do."""
+    S, E = 10, 100
+    _, _, D = orc.synth_dataset(S, E, seed=4)
+    ds = nb.Dataset(D, *orc.nem_constants(0.05, 0.1))
+    n, ladder = 64, 8
+    orders = np.stack([np.random.default_rng(c).permutation(S) for c in range(n)]).astype(np.int32)
+    st = ds.run_chains(orders, 8, 0.3)
+    assert int(st.replica_exchange(ladder, 0, 0).item()) == n // 2        # (0,1),(2,3).. all swap
+    assert int(st.replica_exchange(ladder, 1, 1).item()) == (n // ladder) * (ladder // 2 - 1)  # (1,2),(3,4),(5,6) per ladder
+    gam = np.tile(np.linspace(0.05, 5.0, ladder), n // ladder)
+    st2 = ds.run_chains(orders, 8, gam)
+    s = st2.curr_scores.cpu().numpy(); g = gam
+    expect = sum(min(1.0, np.exp(-((g[i] - g[i + 1]) * (s[i + 1] - s[i])))) for i in range(0, n, 2))
+    got = int(st2.replica_exchange(ladder, 0, 0).item())
+    assert abs(got - expect) <= max(6.0, 4 * np.sqrt(expect))
