@@ -30,6 +30,9 @@ struct nemb200_dataset {
   // one cached CUDA graph of the MCMC iteration body (re-used while the same buffers are passed)
   unsigned long long mcmc_graph_key;
   void *mcmc_graph_exec;  // cudaGraphExec_t
+  // second capture branch of the two-group MCMC loop (created on first use, destroyed with the handle)
+  void *mcmc_side_stream;            // cudaStream_t
+  void *mcmc_ev_fork, *mcmc_ev_join; // cudaEvent_t
 };
 
 void nemb200_set_error(const char *fmt, ...);

@@ -142,6 +142,9 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
 
 extern "C" int nemb200_dataset_destroy(nemb200_dataset *h) {
   if (h && h->mcmc_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->mcmc_graph_exec);
+  if (h && h->mcmc_ev_fork) cudaEventDestroy((cudaEvent_t)h->mcmc_ev_fork);
+  if (h && h->mcmc_ev_join) cudaEventDestroy((cudaEvent_t)h->mcmc_ev_join);
+  if (h && h->mcmc_side_stream) cudaStreamDestroy((cudaStream_t)h->mcmc_side_stream);
   free(h);
   return 0;
 }

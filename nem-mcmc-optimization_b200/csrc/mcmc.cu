@@ -240,9 +240,23 @@ __global__ void k_edge_reduce(const uint32_t *__restrict__ counts, int n, int ce
 
 }  // namespace
 
+// Large runs are split into two chain groups whose iterations are captured as two parallel branches of one
+// CUDA graph: while the score kernel of one group owns the SMs, the (small, latency-bound) propose / accept /
+// finalize kernels of the other group run beside it, so the step time approaches the score time alone.
+// Chains keep their global Philox id, so the result does not depend on the grouping.
+constexpr int kMinChainsForTwoGroups = 512;
+static int first_group_size(const nemb200_dataset *h, int n) {
+  if (n < kMinChainsForTwoGroups || mcmc_fused_preferred(h, n)) return n;
+  const int G = h->G > 0 ? h->G : 1;
+  return ((n / 2 + G - 1) / G) * G;  // whole MMA N tiles in the first group
+}
+
 extern "C" size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_chains) {
   if (!h || n_chains < 0) return 0;
-  return carve(h, n_chains, nullptr, nullptr);
+  const int nA = first_group_size(h, n_chains);
+  size_t one = carve(h, n_chains, nullptr, nullptr);
+  size_t two = nA < n_chains ? carve(h, nA, nullptr, nullptr) + carve(h, n_chains - nA, nullptr, nullptr) : 0;
+  return one > two ? one : two;
 }
 
 static int score_dispatch(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
@@ -295,59 +309,86 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
                    d_accept && d_workspace,
                "null device pointer");
   NEMB_REQUIRE(rule == NEMB200_RULE_FULL || (rule == NEMB200_RULE_MASKED && d_cand_bits), "MASKED rule needs a candidate mask");
-  NEMB_REQUIRE(workspace_bytes >= carve(h, n, nullptr, nullptr), "mcmc workspace too small");
+  NEMB_REQUIRE(workspace_bytes >= nemb200_mcmc_workspace_bytes(h, n), "mcmc workspace too small");
   NEMB_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "mcmc workspace must be 256-byte aligned");
   NEMB_REQUIRE(swap_prob >= 0.0 && swap_prob <= 1.0, "swap_prob must be in [0,1]");
   cudaStream_t st = (cudaStream_t)stream;
-  McmcWs w;
-  carve(h, n, d_workspace, &w);
   const int S = h->S, W = h->W;
   const unsigned long long sp = swap_prob >= 1.0 ? 0x100000000ull : (unsigned long long)(swap_prob * 4294967296.0 + 0.5);
   if (score_impl == NEMB200_MCMC_FUSED || (score_impl == NEMB200_SCORE_AUTO && mcmc_fused_preferred(h, n)))
     return launch_mcmc_fused(h, n, n_iters, iter0, burn_in, d_gamma, sp, seed, chain_offset, rule, d_cand_bits, use_nem,
                              resume, d_orders, d_curr_scores, d_curr_bits, d_best_scores, d_best_orders, d_best_bits,
                              d_accept, d_edge_counts, d_score_trace, st);
-  const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock, thr = kWarpsPerBlock * 32;
+  constexpr int kUnroll = 16;  // iterations per captured CUDA graph
+  const int thr = kWarpsPerBlock * 32;
+  nemb200_dataset *hm = const_cast<nemb200_dataset *>(h);
 
-  auto propose = [&](int init) -> int {
+  // ---- chain groups (see first_group_size)
+  struct Group { int c0, n; McmcWs w; };
+  Group grp[2];
+  int n_groups = 1;
+  const int nA = first_group_size(h, n);
+  if (st != nullptr && nA < n && n_iters >= 2 * kUnroll) n_groups = 2;
+  if (n_groups == 2) {
+    grp[0].c0 = 0; grp[0].n = nA; grp[1].c0 = nA; grp[1].n = n - nA;
+    size_t off = carve(h, nA, d_workspace, &grp[0].w);
+    carve(h, n - nA, (uint8_t *)d_workspace + off, &grp[1].w);
+    if (hm->mcmc_side_stream == nullptr) {
+      cudaStream_t s2; cudaEvent_t e1, e2;
+      NEMB_CHECK_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      hm->mcmc_side_stream = s2;
+      NEMB_CHECK_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+      hm->mcmc_ev_fork = e1;
+      NEMB_CHECK_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+      hm->mcmc_ev_join = e2;
+    }
+  } else {
+    grp[0].c0 = 0; grp[0].n = n;
+    carve(h, n, d_workspace, &grp[0].w);
+  }
+
+  auto step = [&](const Group &g, int init, cudaStream_t s) -> int {
+    const McmcWs &w = g.w;
+    const size_t c0 = (size_t)g.c0;
+    const int grid = (g.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int32_t *orders = d_orders + c0 * S;
+    const uint32_t coff = chain_offset + (uint32_t)g.c0;
     switch (W) {
-      case 1: k_mcmc_propose<1><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
-      case 2: k_mcmc_propose<2><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
-      case 3: k_mcmc_propose<3><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
-      default: k_mcmc_propose<4><<<grid, thr, 0, st>>>(d_orders, n, S, w.iter_a, w.iter_b, seed, chain_offset, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+      case 1: k_mcmc_propose<1><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+      case 2: k_mcmc_propose<2><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+      case 3: k_mcmc_propose<3><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
+      default: k_mcmc_propose<4><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
     }
     NEMB_CHECK_CUDA(cudaGetLastError());
-    return 0;
-  };
-  auto step = [&](int init) -> int {
-    int rc = propose(init);
+    int rc = score_dispatch(h, w.prop_bits, g.n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, s);
     if (rc) return rc;
-    rc = score_dispatch(h, w.prop_bits, n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, st);
-    if (rc) return rc;
-    k_mcmc_accept<<<n, kAcceptThreads, 0, st>>>(n, S, W, w.iter_a, w.iter_b, iter0, burn_in, seed, chain_offset, d_gamma, init,
-                                        w.prop_orders, w.prop_bits, w.prop_scores, d_orders, d_curr_scores, d_curr_bits,
-                                        d_best_scores, d_best_orders, d_best_bits, (long long *)d_accept, d_edge_counts,
-                                        w.since, d_score_trace);
+    // `n` (all chains) is the row stride of the score trace; every other array is passed at the group's offset
+    k_mcmc_accept<<<g.n, kAcceptThreads, 0, s>>>(
+        n, S, W, w.iter_a, w.iter_b, iter0, burn_in, seed, coff, d_gamma + c0, init, w.prop_orders, w.prop_bits,
+        w.prop_scores, orders, d_curr_scores + c0, d_curr_bits + c0 * S * W, d_best_scores + c0, d_best_orders + c0 * S,
+        d_best_bits + c0 * S * W, (long long *)d_accept + c0, d_edge_counts ? d_edge_counts + c0 * S * S : nullptr, w.since,
+        d_score_trace ? d_score_trace + c0 : nullptr);
     NEMB_CHECK_CUDA(cudaGetLastError());
     return 0;
   };
 
-  k_mcmc_init<<<(n + 255) / 256, 256, 0, st>>>(w.iter_a, w.iter_b, w.since, n, iter0);
-  NEMB_CHECK_CUDA(cudaGetLastError());
-  if (!resume) {
-    int rc = step(1);  // method(): score of the start order (:258), best = current
-    if (rc) return rc;
+  for (int gi = 0; gi < n_groups; ++gi) {
+    k_mcmc_init<<<(grp[gi].n + 255) / 256, 256, 0, st>>>(grp[gi].w.iter_a, grp[gi].w.iter_b, grp[gi].w.since, grp[gi].n, iter0);
+    NEMB_CHECK_CUDA(cudaGetLastError());
+    if (!resume) {
+      int rc = step(grp[gi], 1, st);  // method(): score of the start order (:258), best = current
+      if (rc) return rc;
+    }
   }
   // capture kUnroll iterations into a CUDA graph (no host sync per iteration); the legacy NULL stream
   // cannot be captured, so it falls back to direct launches
-  constexpr int kUnroll = 8;
   int64_t done = 0;
   if (st != nullptr && n_iters >= 2 * kUnroll) {
     // the captured body depends only on these arguments (iteration indices live in device memory), so the
     // instantiated graph is cached in the handle and re-used by later calls with the same buffers
     unsigned long long key = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
-    mix((unsigned long long)n); mix((unsigned long long)iter0 * 0 + 17); mix((unsigned long long)burn_in); mix((unsigned long long)(uintptr_t)d_gamma);
+    mix((unsigned long long)n); mix(17ull + (unsigned long long)n_groups); mix((unsigned long long)burn_in); mix((unsigned long long)(uintptr_t)d_gamma);
     mix(sp); mix(seed); mix(chain_offset); mix((unsigned long long)rule); mix((unsigned long long)(uintptr_t)d_cand_bits);
     mix((unsigned long long)use_nem); mix((unsigned long long)score_impl); mix((unsigned long long)(uintptr_t)d_orders);
     mix((unsigned long long)(uintptr_t)d_curr_scores); mix((unsigned long long)(uintptr_t)d_curr_bits);
@@ -356,18 +397,30 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     mix((unsigned long long)(uintptr_t)d_edge_counts); mix((unsigned long long)(uintptr_t)d_score_trace);
     mix((unsigned long long)(uintptr_t)d_workspace); mix((unsigned long long)(uintptr_t)st);
     mix((unsigned long long)iter0 * (d_score_trace != nullptr));  // the trace offset is baked into the kernels
-    nemb200_dataset *hm = const_cast<nemb200_dataset *>(h);
     cudaGraphExec_t exec = (cudaGraphExec_t)hm->mcmc_graph_exec;
     if (exec == nullptr || hm->mcmc_graph_key != key) {
       if (exec) { cudaGraphExecDestroy(exec); hm->mcmc_graph_exec = nullptr; exec = nullptr; }
       cudaGraph_t graph = nullptr;
+      cudaStream_t s2 = (cudaStream_t)hm->mcmc_side_stream;
       NEMB_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       int rc = 0;
-      for (int u = 0; u < kUnroll && rc == 0; ++u) rc = step(0);
+      cudaError_t fe = cudaSuccess;
+      if (n_groups == 2) {  // fork: the side stream joins the capture
+        fe = cudaEventRecord((cudaEvent_t)hm->mcmc_ev_fork, st);
+        if (fe == cudaSuccess) fe = cudaStreamWaitEvent(s2, (cudaEvent_t)hm->mcmc_ev_fork, 0);
+      }
+      for (int u = 0; u < kUnroll && rc == 0 && fe == cudaSuccess; ++u) {
+        rc = step(grp[0], 0, st);
+        if (rc == 0 && n_groups == 2) rc = step(grp[1], 0, s2);
+      }
+      if (n_groups == 2 && fe == cudaSuccess) {  // join
+        fe = cudaEventRecord((cudaEvent_t)hm->mcmc_ev_join, s2);
+        if (fe == cudaSuccess) fe = cudaStreamWaitEvent(st, (cudaEvent_t)hm->mcmc_ev_join, 0);
+      }
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      if (rc != 0 || ce != cudaSuccess) {
+      if (rc != 0 || ce != cudaSuccess || fe != cudaSuccess) {
         if (graph) cudaGraphDestroy(graph);
-        if (rc == 0) nemb200_set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+        if (rc == 0) nemb200_set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : fe));
         return rc ? rc : -2;
       }
       cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
@@ -385,12 +438,18 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     }
   }
   for (; done < n_iters; ++done) {
-    int rc = step(0);
-    if (rc) return rc;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      int rc = step(grp[gi], 0, st);
+      if (rc) return rc;
+    }
   }
   if (d_edge_counts != nullptr) {
-    k_mcmc_flush<<<grid, thr, 0, st>>>(n, S, W, iter0 + n_iters, burn_in, d_curr_bits, d_edge_counts, w.since);
-    NEMB_CHECK_CUDA(cudaGetLastError());
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const size_t c0 = (size_t)grp[gi].c0;
+      k_mcmc_flush<<<(grp[gi].n + kWarpsPerBlock - 1) / kWarpsPerBlock, thr, 0, st>>>(
+          grp[gi].n, S, W, iter0 + n_iters, burn_in, d_curr_bits + c0 * S * W, d_edge_counts + c0 * S * S, grp[gi].w.since);
+      NEMB_CHECK_CUDA(cudaGetLastError());
+    }
   }
   return 0;
 }

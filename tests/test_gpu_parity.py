@@ -511,6 +511,40 @@ def test_sorted_egenes_and_multichain_loop_path(nb):
     assert np.allclose(loop.best_scores[:64], fused.best_scores, rtol=1e-12)
 
 
+def test_mcmc_two_group_overlap_equals_separate_runs(nb):
+    """>= 512 chains run as two chain groups captured as parallel branches of one CUDA graph (csrc/mcmc.cu);
+    chains keep their global Philox id, so the result equals two independent runs of the halves (and the
+    oracle for a few chains), including the score trace, edge counts and a resumed continuation."""
+    S, E = 20, 700
+    _, _, D = orc.synth_dataset(S, E, seed=11)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rng = np.random.default_rng(5)
+    cand = (rng.random((S, S)) < 0.4).astype(np.uint8)
+    n, n_iter, burn, gamma = 602, 77, 10, 2.0 * S / E
+    orders0 = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
+    ds = nb.Dataset(D, A, B)
+    kw = dict(swap_prob=0.9, seed=21, rule=nb.RULE_MASKED, cand=cand, use_nem=True, burn_in=burn, trace=True)
+    st = ds.run_chains(orders0, n_iter, gamma, chain_offset=5, **kw)
+    both = st.result()
+    h = 300
+    lo = ds.run_chains(orders0[:h], n_iter, gamma, chain_offset=5, **kw).result()
+    hi = ds.run_chains(orders0[h:], n_iter, gamma, chain_offset=5 + h, **kw).result()
+    for f in ("best_scores", "best_orders", "curr_orders", "accept_counts", "curr_scores", "best_graphs"):
+        assert np.array_equal(getattr(both, f), np.concatenate([getattr(lo, f), getattr(hi, f)])), f
+    assert np.array_equal(both.score_trace, np.concatenate([lo.score_trace, hi.score_trace], axis=2))
+    assert np.array_equal(both.edge_counts, lo.edge_counts + hi.edge_counts)
+    for c in (0, 299, 300, 301, 601):
+        ref = c_oracle.mcmc_chain(D, A, B, orders0[c], n_iter, gamma, swap_prob=0.9, seed=21, chain=5 + c, rule=1,
+                                  cand=cand, use_nem=True, burn_in=burn, keep_scores=True)
+        _compare_chain(both, c, ref, S)
+    # resumed continuation of the two-group run == one longer run
+    st.run(40, swap_prob=0.9)
+    long = ds.run_chains(orders0, n_iter + 40, gamma, chain_offset=5, **kw).result()
+    cont = st.result()
+    for f in ("best_scores", "curr_orders", "accept_counts", "edge_counts"):
+        assert np.array_equal(getattr(cont, f), getattr(long, f)), f
+
+
 def test_replica_exchange_swap_rate(nb):
     """Swap decisions follow u < exp(-delta) (nem_order_mcmc.py:333-337): with equal gammas delta = 0, so every
     pair swaps; with a wide ladder and spread-out scores fewer do."""
