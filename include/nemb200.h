@@ -37,7 +37,8 @@ enum {
   NEMB200_SCORE_TC_LUT = 2,  /* tcgen05 GEMM + shared-memory exp-table epilogue */
   NEMB200_SCORE_TC_EX2 = 3,  /* tcgen05 GEMM + ex2 epilogue, fixed scale */
   NEMB200_SCORE_TC_EX2_2PASS = 4, /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
-  NEMB200_MCMC_FUSED = 5 /* nemb200_mcmc_run only: persistent one-CTA-per-chain kernel (small S*E) */
+  NEMB200_MCMC_FUSED = 5, /* nemb200_mcmc_run only: persistent one-CTA-per-chain kernel (small S*E) */
+  NEMB200_SCORE_TC_PAIR = 6 /* tcgen05 GEMM + pair-merged table epilogue: two attachment sites per look-up (33 <= S <= 52) */
 };
 
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */

@@ -8,7 +8,10 @@ import os
 import subprocess
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-_SO = os.path.join(_CSRC, "libnemb200.so")
+# NEMB200_LIB_VARIANT=<tag> loads csrc/libnemb200_<tag>.so (diagnostic builds, e.g. "trace" compiled with
+# NEMB200_EXTRA_NVCC_FLAGS=-DNEMB200_TRACE); the product library is libnemb200.so
+_VARIANT = os.environ.get("NEMB200_LIB_VARIANT", "")
+_SO = os.path.join(_CSRC, f"libnemb200_{_VARIANT}.so" if _VARIANT else "libnemb200.so")
 _SOURCES = ["dataset.cu", "graph.cu", "score_tc.cu", "mcmc.cu", "mcmc_fused.cu", "cell.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -28,7 +31,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + srcs
+    extra = os.environ.get("NEMB200_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + srcs
     subprocess.check_call(cmd)
     return _SO
 

@@ -13,7 +13,8 @@
 struct nemb200_dataset {
   int S, E, W;        // S-genes, E-genes, words per bit row
   int KA;             // 64-element K atoms (bf16, SWIZZLE_128B rows of 128 B)
-  int G;              // graphs per MMA N tile
+  int G;              // graphs per MMA N tile (runtime-S kernels: a multiple of 4, or 2)
+  int G_lut;          // graphs per MMA N tile of the specialised table kernel (5 for 48/50-column graphs)
   int CS;             // accumulator columns per graph (S, or S rounded up to 8 for the specialised table kernels)
   int n_mtiles;       // E tiles of 128 rows
   double A, B;        // nem.py:17-18
@@ -24,7 +25,9 @@ struct nemb200_dataset {
   // device pointers (inside the caller's workspace)
   uint32_t *dcol;     // [E_pad][W]  bit i of row e = D[i][e]
   uint8_t *a_lut;     // [n_mtiles][KA][128 x 128 B] bf16 operand image, values {4,256}+bias row
-  uint8_t *a_cnt;     // same shape, values {1,0}
+  uint8_t *a_pair;    // operand image of the pair-merged kernel: 4*D, eight constant rows of 128 and one of 4
+  int pair_ok;        // pair-merged table kernel usable (table valid, 33 <= S <= 52)
+  float *tabs;        // compact exp table of the pair planner: tabs[n(n+1)/2 + p] = lut[n-p][p], n <= S
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)
   double *sumN;       // [1] A * sum(D)   (nem.py:62 summed over e)
   // one cached CUDA graph of the MCMC iteration body (re-used while the same buffers are passed)
@@ -63,7 +66,7 @@ int launch_score_witness(const nemb200_dataset *h, const uint32_t *phi, int n, d
                          cudaStream_t st);
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n);
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                    int impl, cudaStream_t st);
+                    int impl, cudaStream_t st, int leave_sms_free = 0);
 
 bool mcmc_fused_supported(const nemb200_dataset *h);
 bool mcmc_fused_preferred(const nemb200_dataset *h, int n_chains);

@@ -19,7 +19,10 @@ extern "C" int nemb200_version(void) { return NEMB200_VERSION; }
 
 namespace {
 
-struct Layout { size_t dcol, a_lut, lut, sumN, total; int W, n_mtiles; };
+// pair-merged table kernel (score_tc.cu): 32 accumulator columns per graph, S + 9 K rows <= 64
+bool pair_supported(int S) { return S >= 33 && S <= 52; }
+
+struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, sumN, total; int W, n_mtiles; };
 Layout make_layout(int S, int E) {
   Layout L;
   L.W = (S + 31) / 32;
@@ -27,7 +30,9 @@ Layout make_layout(int S, int E) {
   size_t off = 0;
   L.dcol = off; off = align_up(off + (size_t)L.n_mtiles * 128 * L.W * 4, 1024);
   L.a_lut = off; off = align_up(off + (size_t)L.n_mtiles * 128 * 128, 1024);
+  L.a_pair = off; off = align_up(off + (pair_supported(S) ? (size_t)L.n_mtiles * 128 * 128 : 0), 1024);
   L.lut = off; off = align_up(off + 64 * 64 * 4, 1024);
+  L.tabs = off; off = align_up(off + 65 * 66 / 2 * 4, 1024);
   L.sumN = off; off = align_up(off + 8, 1024);
   L.total = off;
   return L;
@@ -47,7 +52,9 @@ __global__ void k_pack_dcol(const uint8_t *D, int S, int E, int W, int E_pad, ui
 
 // u8 A-operand image, one 16 KB SWIZZLE_128B atom per 128 E-genes:
 //   a[e][k] = 2 if D[k][e] else 128 (k < S, e < E); a[e][S] = 128 for every row (exp-table base row); 0 elsewhere
-__global__ void k_build_aimg(const uint32_t *dcol, int S, int E, int W, int E_pad, uint8_t *img) {
+// pair != 0: the image of the pair-merged kernel: a[e][k] = 4*D[k][e]; a[e][S..S+7] = 128, a[e][S+8] = 4 for every row
+// (constant rows: the B operand's entries there add the byte address of the column's table)
+__global__ void k_build_aimg(const uint32_t *dcol, int S, int E, int W, int E_pad, int pair, uint8_t *img) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (row e, 16-byte chunk c)
   if (idx >= E_pad * 8) return;
   int e = idx >> 3, c = idx & 7;
@@ -55,7 +62,11 @@ __global__ void k_build_aimg(const uint32_t *dcol, int S, int E, int W, int E_pa
   for (int b = 0; b < 16; ++b) {
     int k = c * 16 + b;
     uint32_t v = 0;
-    if (k < S && e < E) v = ((dcol[(size_t)e * W + (k >> 5)] >> (k & 31)) & 1u) ? 2u : 128u;
+    if (pair) {
+      if (k < S) v = (e < E && ((dcol[(size_t)e * W + (k >> 5)] >> (k & 31)) & 1u)) ? 4u : 0u;
+      else if (k < S + 8) v = 128u;
+      else if (k == S + 8) v = 4u;
+    } else if (k < S && e < E) v = ((dcol[(size_t)e * W + (k >> 5)] >> (k & 31)) & 1u) ? 2u : 128u;
     else if (k == S) v = 128u;
     bytes[b >> 2] |= v << ((b & 3) * 8);
   }
@@ -78,11 +89,13 @@ __global__ void k_sumN(const uint32_t *dcol, size_t n_words, double A, double *o
 }
 
 // lut[q][p] = 2^(alpha2*p + beta2*q - s) for p+q <= S (0 elsewhere), computed in fp64
-__global__ void k_build_lut(int S, double alpha2, double beta2, double s, float *lut) {
+__global__ void k_build_lut(int S, double alpha2, double beta2, double s, float *lut, float *tabs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 64) return;
-  int q = i >> 6, p = i & 63;
-  lut[i] = (p + q <= S) ? (float)exp2(alpha2 * p + beta2 * q - s) : 0.f;
+  int q = i >> 6, p = i & 63, n = p + q;
+  const float v = (n <= S) ? (float)exp2(alpha2 * p + beta2 * q - s) : 0.f;
+  lut[i] = v;
+  if (n <= S && n < 64) tabs[n * (n + 1) / 2 + p] = v;  // compact copy for the pair planner
 }
 
 }  // namespace
@@ -109,8 +122,8 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   h->CS = S;  // set below once the epilogue kind is known
   h->A = A; h->B = B;
   h->alpha2 = -A * NEMB200_LOG2E; h->beta2 = B * NEMB200_LOG2E;
-  h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_cnt = nullptr;
-  h->lut = (float *)(base + L.lut); h->sumN = (double *)(base + L.sumN);
+  h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_pair = base + L.a_pair;
+  h->lut = (float *)(base + L.lut); h->tabs = (float *)(base + L.tabs); h->sumN = (double *)(base + L.sumN);
   // single-scale validity: largest log2-domain value over the lattice p+q<=S
   double vmax = 0.0;
   if (h->alpha2 > 0) vmax = fmax(vmax, h->alpha2 * S);
@@ -125,11 +138,14 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   if (h->lut_valid && S >= 8 && !(S == 10 || S == 20 || S == 30 || S == 50)) h->CS = (S + 7) / 8 * 8;
   h->G = 256 / h->CS < 16 ? 256 / h->CS : 16;   // graphs per MMA N tile: a multiple of 4 (one quarter per
   h->G = h->G >= 4 ? (h->G & ~3) : 2;           // epilogue warpgroup), or 2 for S > 64
+  h->G_lut = h->G;  // the specialised table kernel may use its own tile width (score_tc.cu: tile_graphs)
   int E_pad = L.n_mtiles * 128;
   k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
-  k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, h->a_lut);
+  k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 0, h->a_lut);
+  h->pair_ok = h->lut_valid && pair_supported(S);
+  if (h->pair_ok) k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 1, h->a_pair);
   k_sumN<<<1, 256, 0, st>>>(h->dcol, (size_t)E_pad * L.W, A, h->sumN);
-  k_build_lut<<<16, 256, 0, st>>>(S, h->alpha2, h->beta2, (double)h->scale, h->lut);
+  k_build_lut<<<16, 256, 0, st>>>(S, h->alpha2, h->beta2, (double)h->scale, h->lut, h->tabs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     free(h);
@@ -151,7 +167,7 @@ extern "C" int nemb200_dataset_destroy(nemb200_dataset *h) {
 
 extern "C" int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int n) {
   NEMB_REQUIRE(h != nullptr && info != nullptr && n >= 8, "dataset_info needs a handle and 8 slots");
-  info[0] = h->S; info[1] = h->E; info[2] = h->W; info[3] = 128; info[4] = h->G;
+  info[0] = h->S; info[1] = h->E; info[2] = h->W; info[3] = 128; info[4] = h->lut_valid ? h->G_lut : h->G;
   info[5] = h->lut_valid; info[6] = h->scale; info[7] = h->n_mtiles;
   return 0;
 }

@@ -5,6 +5,7 @@
 // Randomness: Philox4x32-10, key = seed, counter = (iteration lo, iteration hi, global chain id, 0);
 // word 0 -> swap vs adjacent, words 1,2 -> positions, word 3 -> accept uniform.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -245,9 +246,10 @@ __global__ void k_edge_reduce(const uint32_t *__restrict__ counts, int n, int ce
 // finalize kernels of the other group run beside it, so the step time approaches the score time alone.
 // Chains keep their global Philox id, so the result does not depend on the grouping.
 constexpr int kMinChainsForTwoGroups = 512;
+constexpr int kSmsLeftFree = 20;  // per score launch in two-group mode (measured: 108 vs 126 us/iteration at 1024 chains)
 static int first_group_size(const nemb200_dataset *h, int n) {
   if (n < kMinChainsForTwoGroups || mcmc_fused_preferred(h, n)) return n;
-  const int G = h->G > 0 ? h->G : 1;
+  const int G = h->lut_valid ? h->G_lut : (h->G > 0 ? h->G : 1);
   return ((n / 2 + G - 1) / G) * G;  // whole MMA N tiles in the first group
 }
 
@@ -260,12 +262,12 @@ extern "C" size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_c
 }
 
 static int score_dispatch(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                          int impl, cudaStream_t st) {
+                          int impl, cudaStream_t st, int leave_sms_free = 0) {
   if (impl == NEMB200_SCORE_WITNESS || (impl == NEMB200_SCORE_AUTO && h->S < 8)) {
     NEMB_REQUIRE(ws_bytes >= score_witness_workspace_bytes(n), "score workspace too small");
     return launch_score_witness(h, phi, n, scores, ws, st);
   }
-  return launch_score_tc(h, phi, n, scores, ws, ws_bytes, impl, st);
+  return launch_score_tc(h, phi, n, scores, ws, ws_bytes, impl, st, leave_sms_free);
 }
 
 extern "C" size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs) {
@@ -347,6 +349,8 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     carve(h, n, d_workspace, &grp[0].w);
   }
 
+  static const char *sms_env = getenv("NEMB200_SMS_FREE");  // tuning knob (diagnostics)
+  const int sms_free = sms_env ? atoi(sms_env) : kSmsLeftFree;
   auto step = [&](const Group &g, int init, cudaStream_t s) -> int {
     const McmcWs &w = g.w;
     const size_t c0 = (size_t)g.c0;
@@ -360,7 +364,8 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
       default: k_mcmc_propose<4><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
     }
     NEMB_CHECK_CUDA(cudaGetLastError());
-    int rc = score_dispatch(h, w.prop_bits, g.n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, s);
+    int rc = score_dispatch(h, w.prop_bits, g.n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, s,
+                            n_groups == 2 ? sms_free : 0);
     if (rc) return rc;
     // `n` (all chains) is the row stride of the score trace; every other array is passed at the group's offset
     k_mcmc_accept<<<g.n, kAcceptThreads, 0, s>>>(

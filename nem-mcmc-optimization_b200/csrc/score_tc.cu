@@ -32,33 +32,62 @@
 
 namespace {
 
-constexpr int kThreads = 640;
-constexpr int kStages = 4;
+// Epilogue warpgroups of the specialised table kernel.  Five warpgroups (five 50-column graphs in the 256-column
+// accumulator, 20 epilogue warps, 80 registers) were measured SLOWER than four (111 vs 105 us at S=50, E=10k,
+// 1024 graphs): the kernel is bound by shared-memory bandwidth (look-ups + MMA operand reads + TMA writes), not
+// by the number of warps in flight, so the knob stays at four.
+__host__ __device__ constexpr int epi_warpgroups(int S_T) { return (void)S_T, 4; }
+// graphs per MMA N tile of the specialised kernels
+__host__ __device__ constexpr int tile_graphs(int S_T) {
+  return epi_warpgroups(S_T) == 5 ? 5 : (((256 / S_T) < 16 ? (256 / S_T) : 16) & ~3);
+}
+__host__ __device__ constexpr int cta_threads(int S_T) { return 128 + 128 * (S_T > 0 ? epi_warpgroups(S_T) : 4); }
 constexpr int kTileBytes = 128 * 128;  // one operand atom: 128 rows x 128 B (SWIZZLE_128B)
 constexpr int kLutBytes = 64 * 256;
 constexpr int kMaxG = 16;
 constexpr int kBiasStride = 64;        // floats per graph in the bias array (S <= 128 uses two slots)
 
-// shared memory carve-up (offsets from the 1024-aligned base)
-constexpr int OFF_LUT = 0;                                  // first: its base must be < 32 KB and 128-aligned
-constexpr int OFF_B = OFF_LUT + kLutBytes;                  // 2 buffers x (256 x 128 B)
-constexpr int OFF_A = OFF_B + 2 * 2 * kTileBytes;           // kStages x 16 KB
-constexpr int OFF_BIAS = OFF_A + kStages * kTileBytes;      // 2 buffers x 1024 floats
-constexpr int OFF_ROWS = OFF_BIAS + 2 * 1024 * 4;           // 1024 words of bit rows (expander scratch)
-constexpr int OFF_RED = OFF_ROWS + 1024 * 4;                // 16 warps x 8 doubles
-constexpr int OFF_BAR = OFF_RED + 16 * 8 * 8;               // barriers + scalars
-constexpr int kSmemBytes = OFF_BAR + 256;
+// shared memory carve-up (offsets from the 1024-aligned base).  PAIR = the pair-merged table kernel (below):
+// three A stages, no bias array, a small single-site table and two buffers of per-item pair tables.
+constexpr int kPairCS = 32;                 // accumulator columns per graph of the pair kernel
+constexpr int kPairG = 256 / kPairCS;       // graphs per MMA N tile
+constexpr int kPairCap = 1568;              // table entries per graph (planner cap)
+constexpr int kPairLim = 256;               // table entries per pair (keeps every B weight <= 128)
+constexpr int kPairZero = 2040;             // float index (in the single-site table region) of a permanent 0
+constexpr int kPlanColBytes = 80;           // planner output per accumulator column: 64 B-operand bytes + 16 bytes of meta
+template <bool PAIR>
+struct Lay {
+  static constexpr int STAGES = PAIR ? 3 : 4;
+  static constexpr int LUT = 0;                                   // standard kernel: base must be < 32 KB and 128-aligned
+  static constexpr int LUT_BYTES = PAIR ? 8192 : kLutBytes;
+  static constexpr int B = LUT + LUT_BYTES;                       // 2 buffers x (256 x 128 B)
+  static constexpr int A = B + 2 * 2 * kTileBytes;                // STAGES x 16 KB
+  static constexpr int BIAS = A + STAGES * kTileBytes;            // 2 buffers x 1024 floats (ex2 epilogues)
+  static constexpr int ROWS = BIAS + (PAIR ? 0 : 2 * 1024 * 4);   // 1024 words of bit rows (+ 512 words of scan scratch)
+  static constexpr int RED = ROWS + 1024 * 4 + (PAIR ? 2048 : 0); // 20 warps x 8 doubles
+  static constexpr int BAR = RED + 20 * 8 * 8;                    // barriers + scalars
+  static constexpr int TAB = BAR + 256;                           // PAIR: 2 buffers of pair tables
+  static constexpr int TAB_BYTES = PAIR ? kPairG * kPairCap * 4 : 0;
+  static constexpr int BYTES = TAB + 2 * TAB_BYTES;
+};
+static_assert(Lay<true>::BYTES <= 232448 && Lay<false>::BYTES <= 232448, "shared memory budget");
 
 struct Params {
   const uint32_t *phi;   // [n_graphs][S][W]
   const uint8_t *a_img;  // [n_mtiles][16 KB]
   const float *lut;      // [64][64]
-  double *partials;      // [n_ntiles*G][n_chunks]
-  int n_graphs, S, W, E, G, n_ntiles, n_mtiles, tpc, n_chunks, n_items, nmma, ksteps;
+  double *partials;      // [n_ntiles*G][n_slots]
+  int n_graphs, S, W, E, G, n_mtiles, n_slots, nmma, ksteps;
   int CS;                // accumulator columns per graph (>= S; the specialised kernels pad S up to a multiple of 8)
   float k1;              // EX2: x = k1 * acc + bias_j
   float kc;              // EX2: bias_j = kc * c_j - s
   float scale;           // s
+  // pair kernel: per graph kPairCS columns of (site, partner or 255); 255,255 = padding column
+  const uint8_t *plan;
+  const float *tables;   // pair kernel: per graph kPairCap floats (the graph's pair tables, built by the planner)
+  // list mode (fallback pass of the pair kernel): graph ids and their count live in device memory
+  const int *glist;
+  const int *n_dev;
   long long *trace;      // diagnostics only: clock64 time line of CTA 0 (NULL normally)
   int debug;             // diagnostics only (NEMB200_DEBUG): 1 skip epilogue math, 2 skip MMA, 4 skip TMA, 8 skip expansion
 };
@@ -166,6 +195,66 @@ __device__ __forceinline__ float log2_split(float x) {
 
 enum { EPI_LUT = 0, EPI_EX2 = 1, EPI_EX2_2PASS = 2 };
 
+// Named barrier of one epilogue warpgroup (ids 1..5).  The id is an immediate on purpose: with a register operand
+// ptxas reserves all 16 hardware barriers for the kernel, and then no CTA that uses __syncthreads() (the MCMC accept
+// kernel of the other chain group) can be co-resident with a score CTA.
+__device__ __forceinline__ void wg_bar_sync(int wg) {
+  switch (wg) {
+    case 0: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 128;" ::: "memory"); break;
+  }
+}
+
+// ---- work distribution ---------------------------------------------------------------------------
+// The (N tile, E tile) grid is flattened N-tile-major and cut into `ctas` equal contiguous ranges, one per
+// CTA, so every CTA gets the same number of tiles (+-1) whatever the batch size.  A CTA's range is a
+// sequence of "items" (runs of E tiles inside one N tile: one B-operand expansion each); an N tile cut by CTA
+// boundaries gives one partial sum per piece ("slot" = CTA index - first CTA of that N tile).
+constexpr int kMinTilesPerCta = 20;  // a CTA gets at least ceil(n_mtiles / 20) tiles: at most 22 slots per N tile
+constexpr int kMaxSlots = 24;
+__host__ __device__ inline int effective_ctas(unsigned T, int n_mtiles, int max_ctas) {
+  const unsigned pmin = (unsigned)(n_mtiles + kMinTilesPerCta - 1) / kMinTilesPerCta;
+  unsigned c = T / (pmin > 0 ? pmin : 1u);
+  if (c < 1) c = 1;
+  return (int)(c < (unsigned)max_ctas ? c : (unsigned)max_ctas);
+}
+// first flat tile of CTA c: ranges [c*T/ctas, (c+1)*T/ctas); T * ctas < 2^32 is checked by the host
+__host__ __device__ inline unsigned cta_first_tile(unsigned c, unsigned T, unsigned ctas) { return (unsigned)(((unsigned long long)c * T) / ctas); }
+__host__ __device__ inline int cta_of_tile(unsigned x, unsigned T, unsigned ctas) {  // owner of flat tile x
+  return (int)(((unsigned long long)(x + 1) * ctas + T - 1) / T) - 1;
+}
+__host__ __device__ inline int slots_of_ntile(int ntile, int n_mtiles, unsigned T, int ctas) {
+  const unsigned lo = (unsigned)ntile * (unsigned)n_mtiles;
+  return cta_of_tile(lo + n_mtiles - 1, T, ctas) - cta_of_tile(lo, T, ctas) + 1;
+}
+struct Item { int ntile, m0, nt; };
+struct Walker {  // two registers of state: every role walks the same item sequence
+  unsigned pos, end;
+  __device__ __forceinline__ Walker(int n_ntiles, int n_mtiles, int max_ctas, int cta) {
+    const unsigned T = (unsigned)n_ntiles * (unsigned)n_mtiles;
+    const int ctas = effective_ctas(T, n_mtiles, max_ctas);
+    pos = cta < ctas ? cta_first_tile(cta, T, ctas) : 0u;
+    end = cta < ctas ? cta_first_tile(cta + 1, T, ctas) : 0u;
+  }
+  __device__ __forceinline__ bool next(Item &it, int n_mtiles) {
+    if (pos >= end) return false;
+    it.ntile = (int)(pos / (unsigned)n_mtiles);
+    it.m0 = (int)(pos - (unsigned)it.ntile * (unsigned)n_mtiles);
+    const unsigned rem = end - pos;
+    it.nt = (unsigned)(n_mtiles - it.m0) < rem ? n_mtiles - it.m0 : (int)rem;
+    pos += (unsigned)it.nt;
+    return true;
+  }
+};
+// partial-sum slot of this CTA inside N tile `ntile`
+__device__ __forceinline__ int item_slot(int ntile, int n_ntiles, int n_mtiles, int max_ctas, int cta) {
+  const unsigned T = (unsigned)n_ntiles * (unsigned)n_mtiles;
+  return cta - cta_of_tile((unsigned)ntile * (unsigned)n_mtiles, T, effective_ctas(T, n_mtiles, max_ctas));
+}
+
 // diagnostics (compile with -DNEMB200_TRACE): time line slots [role 0..3][tile 0..255][event 0..3]
 #ifdef NEMB200_TRACE
 #define DBG(flag) (p.debug & (flag))
@@ -264,7 +353,7 @@ __device__ __forceinline__ void finalize_pending(Pending &pd, const Params &p, d
   pd.valid = false;
 }
 
-template <int S_T, int NLUT, int C0, int C1>
+template <int S_T, int NLUT, int C0, int C1, int SHIFT = 0>
 __device__ __forceinline__ void static_cols(const uint32_t (&r)[32], const float *sBias, const Params &p, bool valid,
                                             int ng_mine, float (&acc)[4], float4 &b4, float null_term, Pending &pd,
                                             double (&part)[kMaxG / 4]) {
@@ -274,13 +363,13 @@ __device__ __forceinline__ void static_cols(const uint32_t (&r)[32], const float
     if (j == 0) { acc[0] = null_term; acc[1] = 0.f; acc[2] = 0.f; acc[3] = 0.f; }
     float v;
     if (is_lut_site<S_T, NLUT>(j)) {
-      v = lds_f32(r[col - C0]);
+      v = lds_f32(r[col - C0 + SHIFT]);
     } else {
       // (re)load the float4 of biases that holds site j (ex2 groups start on a 16-byte boundary)
       if ((j & 3) == 0 || col == C0) b4 = *reinterpret_cast<const float4 *>(sBias + g * kBiasStride + (j & ~3));
       const int w = j & 3;
       const float b = w == 0 ? b4.x : (w == 1 ? b4.y : (w == 2 ? b4.z : b4.w));
-      v = ex2f(fmaf((float)(int)r[col - C0], p.k1, b));
+      v = ex2f(fmaf((float)(int)r[col - C0 + SHIFT], p.k1, b));
     }
     if (j == 8 || (S_T <= 8 && j == S_T - 1)) finalize_pending(pd, p, part);  // previous graph, mid-stream
     acc[j & 3] += v;
@@ -297,10 +386,16 @@ template <int S_T, int NLUT>
 __device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem_cols, const float *sBias, int ng_mine,
                                                   int row0, int nt, uint32_t it0, uint32_t bar_tfull, uint32_t bar_tempty,
                                                   double (&part)[kMaxG / 4]) {
-  constexpr int G = ((256 / S_T) < kMaxG ? (256 / S_T) : kMaxG) & ~3;
-  constexpr int NCOL = (G / 4) * S_T;  // this warpgroup's quarter of the tile's graphs
+  constexpr int G = tile_graphs(S_T);
+  constexpr int NCOL = (G / epi_warpgroups(S_T)) * S_T;  // this warpgroup's share of the tile's graphs
   constexpr int NA = NCOL < 32 ? NCOL : 32, NB = NCOL - NA;
   static_assert(NCOL <= 64, "a warpgroup's share must fit two 32-column TMEM loads");
+  // The second load is 8, 16 or 32 columns wide and ENDS at the warpgroup's last column (it never reads past
+  // the warpgroup's share, so the last warpgroup stays inside the 256-column buffer); its first BSH registers
+  // repeat columns of chunk A and are ignored.
+  constexpr int NBL = NB > 16 ? 32 : (NB > 8 ? 16 : 8);
+  constexpr int BSTART = NB > 0 ? NCOL - NBL : 0, BSH = NB > 0 ? NA - BSTART : 0;
+  static_assert(NB == 0 || BSTART >= 0, "second TMEM load would start before the warpgroup's share");
   const int lane = threadIdx.x & 31;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -326,7 +421,7 @@ __device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem
     ETRACE(0);
     tmem_wait_ld();  // A(t) is in registers
     ETRACE(1);
-    if (NB > 0) TMEM_LDN(NB, tmem_cols + buf * 256u + 32u, rb);
+    if (NB > 0) TMEM_LDN(NB, tmem_cols + buf * 256u + (uint32_t)BSTART, rb);
     static_cols<S_T, NLUT, 0, NA>(ra, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
     ETRACE(2);
     const uint32_t itn = it0 + (uint32_t)t + 1u, nbuf = itn & 1u;
@@ -346,31 +441,36 @@ __device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem
       TMEM_LDN(NA, tmem_cols + buf * 256u, ra);
     }
     ETRACE(6);
-    if (NB > 0) static_cols<S_T, NLUT, NA, NCOL>(rb, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
+    if (NB > 0) static_cols<S_T, NLUT, NA, NCOL, BSH>(rb, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
     ETRACE(7);
   }
   finalize_pending(pd, p, part);
 #undef ETRACE
 }
 
-template <int EPI, int S_T, int NLUT>
-__global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
+template <int EPI, int S_T, int NLUT, bool PAIR = false>
+__global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p) {
+  constexpr int NWG = S_T > 0 ? epi_warpgroups(S_T) : 4;
+  using L = Lay<PAIR>;
+  constexpr int kStages = L::STAGES;
+  static_assert(!PAIR || (EPI == EPI_LUT && S_T == kPairCS), "the pair kernel is the 32-column table kernel");
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (p.n_dev != nullptr && *p.n_dev == 0) return;  // list mode with an empty list: nothing to do (uniform exit)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::BAR);
   // barrier map: a_full[4] a_empty[4] t_full[2] t_empty[2] b_full[2] e_done[2]
-  const uint32_t bar_afull = sbase + OFF_BAR, bar_aempty = bar_afull + 8 * kStages, bar_tfull = bar_aempty + 8 * kStages,
+  const uint32_t bar_afull = sbase + L::BAR, bar_aempty = bar_afull + 8 * 4, bar_tfull = bar_aempty + 8 * 4,
                  bar_tempty = bar_tfull + 16, bar_bfull = bar_tempty + 16, bar_edone = bar_bfull + 16;
-  volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(bars + 2 * kStages + 8);
-  uint32_t *sRows = reinterpret_cast<uint32_t *>(smem + OFF_ROWS);
-  double *sRed = reinterpret_cast<double *>(smem + OFF_RED);
+  volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(bars + 2 * 4 + 8);
+  uint32_t *sRows = reinterpret_cast<uint32_t *>(smem + L::ROWS);
+  double *sRed = reinterpret_cast<double *>(smem + L::RED);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bar_afull + 8 * i, 1); mbar_init(bar_aempty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 16);
-      mbar_init(bar_bfull + 8 * i, 2); mbar_init(bar_edone + 8 * i, 16);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4 * NWG);
+      mbar_init(bar_bfull + 8 * i, 2); mbar_init(bar_edone + 8 * i, 4 * NWG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -378,32 +478,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void *)s_tmem)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (EPI == EPI_LUT)
-    for (int i = threadIdx.x; i < kLutBytes / 4; i += kThreads) reinterpret_cast<float *>(smem + OFF_LUT)[i] = p.lut[i];
+  if constexpr (PAIR) {
+    // single-site table, compact: tabS[n(n+1)/2 + p] = 2^(alpha2*p + beta2*(n-p) - s) = lut[n-p][p]; the rest of the region is 0
+    float *tabS = reinterpret_cast<float *>(smem + L::LUT);
+    for (int i = threadIdx.x; i < L::LUT_BYTES / 4; i += cta_threads(S_T)) tabS[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += cta_threads(S_T)) {
+      const int q = i >> 6, pp = i & 63, n = pp + q;
+      if (n <= p.S) tabS[n * (n + 1) / 2 + pp] = p.lut[i];
+    }
+  } else if (EPI == EPI_LUT) {
+    for (int i = threadIdx.x; i < kLutBytes / 4; i += cta_threads(S_T)) reinterpret_cast<float *>(smem + L::LUT)[i] = p.lut[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const int S = p.S, W = p.W, G = p.G;
+  // list mode: the graph count (and with it the item count) is only known on the device
+  const int n_graphs = p.n_dev != nullptr ? *p.n_dev : p.n_graphs;
+  const int n_ntiles = (n_graphs + G - 1) / G;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32 (2<<4), A=B=U8 (0), K-major, N>>3 at 17, M>>4 at 24
   const uint32_t idesc = (2u << 4) | ((uint32_t)(p.nmma >> 3) << 17) | ((128u >> 4) << 24);
-  const int n_my_items = p.n_items > (int)blockIdx.x ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     // =============================== TMA producer: A tiles of every item, in order ===================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int k = 0; k < n_my_items; ++k) {
-        const int item = (int)blockIdx.x + k * (int)gridDim.x;
-        const int chunk = item / p.n_ntiles;
-        const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
+      Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
+      Item im;
+      while (wk.next(im, p.n_mtiles)) {
+        const int m0 = im.m0, nt = im.nt;
         for (int t = 0; t < nt; ++t, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1u;
           mbar_wait(bar_aempty + 8 * st, ph ^ 1u);
           TRACE(0, it, 0);
           if (DBG(4)) { mbar_arrive(bar_afull + 8 * st); continue; }
-          mbar_expect_tx(bar_afull + 8 * st, kTileBytes);
-          bulk_g2s(sbase + OFF_A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, kTileBytes, bar_afull + 8 * st);
+          const uint32_t tma_bytes = DBG(16) ? kTileBytes / 2 : kTileBytes;  // diagnostics: half the operand traffic (wrong results)
+          mbar_expect_tx(bar_afull + 8 * st, tma_bytes);
+          bulk_g2s(sbase + L::A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, tma_bytes, bar_afull + 8 * st);
         }
       }
     }
@@ -411,13 +524,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
     // =============================== MMA issuer =======================================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int k = 0; k < n_my_items; ++k) {
-        const int item = (int)blockIdx.x + k * (int)gridDim.x;
-        const int chunk = item / p.n_ntiles;
-        const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
+      Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
+      Item im;
+      for (int k = 0; wk.next(im, p.n_mtiles); ++k) {
+        const int nt = im.nt;
         const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
         mbar_wait(bar_bfull + 8 * bb, bbph);  // this item's B operand is expanded
-        const uint32_t b0 = sbase + OFF_B + bb * 2 * kTileBytes;
+        const uint32_t b0 = sbase + L::B + bb * 2 * kTileBytes;
         for (int t = 0; t < nt; ++t, ++it) {
           const uint32_t st = it % kStages, ph = (it / kStages) & 1u, buf = it & 1u, bph = (it >> 1) & 1u;
           TRACE(1, it, 0);
@@ -426,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
           mbar_wait(bar_tempty + 8 * buf, bph ^ 1u);
           TRACE(1, it, 2);
           tc_fence_after();
-          const uint32_t a0 = sbase + OFF_A + st * kTileBytes;
+          const uint32_t a0 = sbase + L::A + st * kTileBytes;
           for (int ks = 0; ks < (DBG(2) ? 0 : p.ksteps); ++ks)
             umma_i8(tmem_base + buf * 256u, umma_desc(a0 + ks * 32), umma_desc(b0 + ks * 32), idesc, ks > 0 ? 1u : 0u);
           umma_commit(bar_aempty + 8 * st);  // A slot reusable once these MMAs retire
@@ -438,17 +551,58 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
   } else if (warp < 4) {
     // =============================== B expanders (64 threads, one item ahead) ==========================
     const int te = threadIdx.x - 64;
-    for (int k = 0; k < n_my_items; ++k) {
-      const int item = (int)blockIdx.x + k * (int)gridDim.x;
-      const int ntile = item % p.n_ntiles;
-      const int g0 = ntile * G, ng = min(G, p.n_graphs - g0);
+    Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
+    Item im;
+    for (int k = 0; wk.next(im, p.n_mtiles); ++k) {
+      const int ntile = im.ntile;
+      const int g0 = ntile * G, ng = min(G, n_graphs - g0);
       const uint32_t bb = k & 1u;
       if (k >= 2) mbar_wait(bar_edone + 8 * bb, ((k - 2) >> 1) & 1u);  // epilogue finished the item that used this buffer
-      const int nwords = ng * S * W;
-      for (int i = te; i < nwords; i += 64) sRows[i] = p.phi[(size_t)g0 * S * W + i];
-      asm volatile("bar.sync 5, 64;" ::: "memory");
-      uint8_t *brow = smem + OFF_B + bb * 2 * kTileBytes;
-      float *bias = reinterpret_cast<float *>(smem + OFF_BIAS) + bb * 1024;
+      const int gw = S * W;  // words per graph
+      for (int i = te; i < (PAIR ? 0 : ng * gw); i += 64) {
+        const int gi = i / gw;
+        const int gid = p.glist != nullptr ? p.glist[g0 + gi] : g0 + gi;
+        sRows[i] = p.phi[(size_t)gid * gw + (i - gi * gw)];
+      }
+      asm volatile("bar.sync 6, 64;" ::: "memory");
+      uint8_t *brow = smem + L::B + bb * 2 * kTileBytes;
+      if constexpr (PAIR) {
+        // ---- pair-merged columns: the planner (k_pair_plan) wrote every column's 64 operand bytes and the shape
+        // of its table; here the constant K rows get the table's shared-memory address and the pair tables of
+        // this item are built (graph gi owns a fixed slot of kPairCap entries in table buffer bb)
+        const uint32_t tab_addr = sbase + L::TAB + bb * L::TAB_BYTES, tabs_addr = sbase + L::LUT;
+        uint32_t *sTot = sRows;  // table entries per graph of this item
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int col = te + 64 * u, gi = col / kPairCS, c = col - gi * kPairCS;
+          uint4 v[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          uint4 meta = make_uint4(0, 0, 0, 0);
+          if (gi < ng) {
+            const int gid = p.glist != nullptr ? p.glist[g0 + gi] : g0 + gi;
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.plan + ((size_t)gid * kPairCS + c) * kPlanColBytes);
+            v[0] = src[0]; v[1] = src[1]; v[2] = src[2]; v[3] = src[3]; meta = src[4];
+          }
+          const int kind = (int)(meta.x & 255u), n1 = (int)((meta.x >> 8) & 255u), nC = (int)(meta.x >> 24),
+                    d1 = (int)(meta.y & 255u), d2 = (int)((meta.y >> 8) & 255u);
+          const uint32_t toff = (uint32_t)gi * kPairCap + (meta.y >> 16);
+          if (kind == 2 && (meta.y >> 16) + (uint32_t)((nC + 1) * (d1 + 1) * (d2 + 1)) > (uint32_t)kPairCap) asm volatile("trap;");
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)cc * 16u)) = v[cc];
+          // byte address of the column's table entry 0 -> K rows S..S+7 (x128) and S+8 (x4)
+          const uint32_t addr = kind == 2 ? tab_addr + 4u * toff
+                                          : (kind == 1 ? tabs_addr + 4u * (uint32_t)(n1 * (n1 + 1) / 2) : tabs_addr + 4u * kPairZero);
+          uint32_t q = addr >> 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t b = q < 255u ? q : 255u;
+            q -= b;
+            brow[sw128((uint32_t)col, (uint32_t)(S + i))] = (uint8_t)b;
+          }
+          brow[sw128((uint32_t)col, (uint32_t)(S + 8))] = (uint8_t)((addr & 127u) >> 2);
+          if (c == 0) sTot[gi] = meta.z;  // table entries of graph gi (0 for absent / unplanned graphs)
+        }
+      } else {
+      float *bias = reinterpret_cast<float *>(smem + L::BIAS) + bb * 1024;
       const int bstride = kBiasStride * (S > 64 ? 2 : 1);
       const int CS = p.CS;
       // padding sites (S <= j < CS) of the specialised kernels look up a table entry that is zero:
@@ -481,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
           v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
           v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
           if (lut_site && c == (S >> 4)) {
-            uint32_t extv = ((sbase + OFF_LUT) >> 7) + (j >= S ? zero_m : 0u);
+            uint32_t extv = ((sbase + L::LUT) >> 7) + (j >= S ? zero_m : 0u);
             if (extv > 255u) asm volatile("trap;");  // the table must sit in the first 32 KB of shared memory
             uint32_t ext = extv << ((S & 3) * 8);
             int wsel = (S >> 2) & 3;
@@ -491,27 +645,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
         }
         if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
       }
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_bfull + 8 * bb);
-      asm volatile("bar.sync 5, 64;" ::: "memory");  // sRows is reused by the next item
+      if constexpr (PAIR) {
+        // the planner left every graph's pair tables in global memory: one bulk copy per graph into its slot of
+        // table buffer bb, completing on the same barrier as the operand (the epilogue waits on it)
+        asm volatile("bar.sync 6, 64;" ::: "memory");  // sTot is complete
+        if (warp == 2 && lane == 0) {
+          uint32_t bytes = 0;
+          for (int gi = 0; gi < ng; ++gi) bytes += (sRows[gi] * 4u + 15u) & ~15u;
+          mbar_expect_tx(bar_bfull + 8 * bb, bytes);
+          for (int gi = 0; gi < ng; ++gi) {
+            const uint32_t nb = (sRows[gi] * 4u + 15u) & ~15u;
+            const int gid = p.glist != nullptr ? p.glist[g0 + gi] : g0 + gi;
+            if (nb) bulk_g2s(sbase + L::TAB + bb * L::TAB_BYTES + (uint32_t)gi * kPairCap * 4u, p.tables + (size_t)gid * kPairCap, nb,
+                             bar_bfull + 8 * bb);
+          }
+        } else if (lane == 0) {
+          mbar_arrive(bar_bfull + 8 * bb);
+        }
+      } else {
+        if (lane == 0) mbar_arrive(bar_bfull + 8 * bb);
+      }
+      asm volatile("bar.sync 6, 64;" ::: "memory");  // sRows is reused by the next item
     }
   } else {
     // =============================== epilogue: 4 warpgroups share every tile, a quarter of its graphs each ===
     const int wg = (warp - 4) >> 2, quarter = warp & 3, tw = threadIdx.x - 128 - wg * 128;
-    const int gq = G >= 4 ? (G >> 2) : 1;                        // graphs per warpgroup (G == 2: warpgroups 2,3 idle)
+    const int gq = G >= NWG ? G / NWG : 1;                       // graphs per warpgroup (G == 2: warpgroups 2,3 idle)
     const int bstride = kBiasStride * (S > 64 ? 2 : 1);
     uint32_t it = 0;
-    for (int k = 0; k < n_my_items; ++k) {
-      const int item = (int)blockIdx.x + k * (int)gridDim.x;
-      const int chunk = item / p.n_ntiles, ntile = item % p.n_ntiles;
-      const int m0 = chunk * p.tpc, nt = min(p.tpc, p.n_mtiles - m0);
+    Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
+    Item im;
+    for (int k = 0; wk.next(im, p.n_mtiles); ++k) {
+      const int ntile = im.ntile, m0 = im.m0, nt = im.nt;
       const int gl = wg * gq;                                     // first graph (within the tile) of this warpgroup
       const int g0 = ntile * G + gl;
-      const int ng_mine = gl < G ? max(0, min(gq, p.n_graphs - g0)) : 0;
+      const int ng_mine = gl < G ? max(0, min(gq, n_graphs - g0)) : 0;
       const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
-      const float *bias = reinterpret_cast<const float *>(smem + OFF_BIAS) + bb * 1024 + gl * bstride;
-      mbar_wait(bar_bfull + 8 * bb, bbph);  // bias values of this item are written
+      const float *bias = reinterpret_cast<const float *>(smem + L::BIAS) + bb * 1024 + gl * bstride;
+      mbar_wait(bar_bfull + 8 * bb, bbph);  // bias values (pair kernel: tables) of this item are written
       double part[kMaxG / 4];
 #pragma unroll
       for (int g = 0; g < kMaxG / 4; ++g) part[g] = 0.0;
@@ -547,13 +721,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_edone + 8 * bb);  // bias / B buffer of this item may be recycled
-      asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+      wg_bar_sync(wg);
       if (tw < ng_mine) {
         double v = 0.0;
         for (int w4 = 0; w4 < 4; ++w4) v += sRed[(wg * 4 + w4) * 8 + tw];
-        p.partials[(size_t)(g0 + tw) * p.n_chunks + chunk] = v;
+        p.partials[(size_t)(g0 + tw) * p.n_slots + item_slot(ntile, n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x)] = v;  // list mode: indexed by list position
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+      wg_bar_sync(wg);
     }
   }
   tc_fence_before();
@@ -561,36 +735,222 @@ __global__ void __launch_bounds__(kThreads, 1) k_score_tc(const Params p) {
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
-__global__ void k_finalize(const double *partials, int n_slots, const double *sumN, int n_graphs, double *scores) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_graphs) return;
-  double v = 0.0;
-  for (int c = 0; c < n_slots; ++c) v += partials[(size_t)g * n_slots + c];
-  scores[g] = *sumN + NEMB200_LN2 * v;
+// ---- pair planner --------------------------------------------------------------------------------------
+// The epilogue is bound by shared-memory look-ups: one per (attachment site, E-gene).  Two sites j, j' whose
+// ancestor sets A, A' overlap can share ONE look-up: with C = A & A', D1 = A \ C, D2 = A' \ C the pair's term
+//     2^x_j + 2^x_j' = V(|A|, pc + p1) + V(|A'|, pc + p2),   V(n, p) = 2^(alpha2*p + beta2*(n-p) - s)
+// depends on the E-gene only through the three counts pc, p1, p2 of ones among C, D1, D2.  A B-operand column
+// with weights 1 on C, w1 = |C|+1 on D1 and w2 = w1*(|D1|+1) on D2 makes the accumulator the mixed-radix index
+// pc + w1*p1 + w2*p2 into a per-pair table of (|C|+1)(|D1|+1)(|D2|+1) entries that the expander warps build in
+// shared memory (constant K rows add the table's address, as in the single-site kernel).  The planner (one
+// warp per graph) pairs sites greedily in order of ancestor count, keeps the S - 32 cheapest pairs (tables of
+// at most kPairLim entries, kPairCap per graph) and leaves the other sites single: a 50-site graph becomes 32
+// accumulator columns.  Graphs that cannot be planned are appended to a list and scored by the one-site kernel.
+constexpr int kPlanThreads = 256;  // one CTA per graph; the planner is latency-bound, so phases are spread over many threads
+__global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__restrict__ phi, int n, int S, int W,
+                                                           const float *__restrict__ tabs, uint8_t *__restrict__ plan,
+                                                           float *__restrict__ tables, int *__restrict__ fbslot,
+                                                           int *__restrict__ flist, int *__restrict__ fcount,
+                                                           long long *__restrict__ trace) {
+#define PTRACE(k) do { if (trace != nullptr && blockIdx.x == 500 && threadIdx.x == 0) trace[k] = clock64(); } while (0)
+  __shared__ uint32_t s_rows[64 * 2];
+  __shared__ uint4 s_site[64];    // by site j:            {mask word 0, mask word 1, ancestor count, j}
+  __shared__ uint4 s_sorted[64];  // by sorted position r: the same record of the r-th smallest site
+  __shared__ uint4 s_col[kPairCS];  // by accumulator column: {kind, n1 | n2 << 8 | nC << 16, table offset, -}
+  __shared__ uint8_t s_plan[2 * kPairCS];
+  __shared__ uint16_t s_cost[64][32];  // pair cost of sorted positions (a, a+1+w), 0xFFFF = not allowed
+  __shared__ float s_tab[57 * 58 / 2];  // V(n, p) = lut[n-p][p] at n(n+1)/2 + p, n <= S <= 56
+  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  PTRACE(0);
+  for (int i = tid; i < S * W; i += kPlanThreads) s_rows[i] = phi[(size_t)g * S * W + i];
+  for (int i = tid; i < (S + 1) * (S + 2) / 2; i += kPlanThreads) s_tab[i] = tabs[i];
+  __syncthreads();
+  PTRACE(1);
+  // ancestor-or-self masks (columns of I | Phi): thread (site j, quarter qr) builds 16 bits = rows 16qr .. 16qr+15
+  {
+    const int j = tid & 63, qr = tid >> 6;
+    uint32_t m = 0;
+    if (j < S) {
+      const int a_end = min(S, 16 * qr + 16);
+      for (int a = 16 * qr; a < a_end; ++a) {
+        const uint32_t bit = ((s_rows[a * W + (j >> 5)] >> (j & 31)) & 1u) | (a == j ? 1u : 0u);
+        m |= bit << (a & 15);
+      }
+    }
+    reinterpret_cast<uint16_t *>(&s_site[j])[qr] = (uint16_t)m;
+    if (qr == 0) s_sorted[j] = make_uint4(0u, 0u, 1u << 20, 255u);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const uint4 v = s_site[tid];
+    s_site[tid] = make_uint4(v.x, v.y, tid < S ? (uint32_t)(__popc(v.x) + __popc(v.y)) : (1u << 20), (uint32_t)tid);
+  }
+  __syncthreads();
+  PTRACE(2);
+  // sorted by (ancestor count, index)
+  if (tid < S) {
+    const uint4 me = s_site[tid];
+    int r = 0;
+#pragma unroll 4
+    for (int k = 0; k < S; ++k) { const uint32_t nk = s_site[k].z; r += (nk < me.z || (nk == me.z && k < tid)) ? 1 : 0; }
+    s_sorted[r] = me;
+  }
+  __syncthreads();
+  PTRACE(3);
+  // all pair costs inside the window, in parallel: thread (a, wq) takes partners a+1+wq, a+1+wq+4, ..
+  {
+    const int a = tid >> 2, wq = tid & 3;
+    const uint4 si = s_sorted[a];
+#pragma unroll
+    for (int w = wq; w < 32; w += 4) {
+      const int idx = a + 1 + w;
+      uint32_t cost = 0xFFFFu;
+      if (a < S && idx < S) {
+        const uint4 sj = s_sorted[idx];
+        const int nC = __popc(si.x & sj.x) + __popc(si.y & sj.y);
+        const uint32_t c = (uint32_t)((nC + 1) * ((int)si.z - nC + 1) * ((int)sj.z - nC + 1));
+        if (c <= (uint32_t)kPairLim) cost = c;
+      }
+      s_cost[a][w] = (uint16_t)cost;
+    }
+  }
+  __syncthreads();
+  PTRACE(4);
+  const int need = S - kPairCS;
+  if (warp == 0) {
+    // greedy matching over sorted positions: the first free position takes the cheapest free partner among the next 32
+    uint32_t u0 = 0, u1 = S >= 64 ? 0u : ~((S > 32 ? (1u << (S - 32)) : 1u) - 1u);  // positions >= S are "used"
+    if (S <= 32) { u0 = S == 32 ? 0u : ~((1u << S) - 1u); u1 = 0xffffffffu; }
+    int npairs = 0;
+    uint32_t my_cost = 0xFFFFFFFFu, my_a = 0, my_b = 0;  // lane k keeps pair k
+    while (true) {
+      const int a = ~u0 ? __ffs(~u0) - 1 : (~u1 ? 32 + __ffs(~u1) - 1 : 64);
+      if (a >= S - 1) break;
+      if (a < 32) u0 |= 1u << a; else u1 |= 1u << (a - 32);  // paired below or left single
+      const int idx = a + 1 + lane;
+      const uint32_t c = s_cost[a][lane];
+      const bool taken = idx >= 64 || ((((idx < 32 ? u0 : u1) >> (idx & 31)) & 1u) != 0u);
+      const uint32_t packed = (c == 0xFFFFu || taken) ? 0xFFFFFFFFu : ((c << 8) | (uint32_t)lane);
+      const uint32_t best = __reduce_min_sync(0xffffffffu, packed);
+      if (best == 0xFFFFFFFFu) continue;
+      const int b = a + 1 + (int)(best & 255u);
+      if (b < 32) u0 |= 1u << b; else u1 |= 1u << (b - 32);
+      if (lane == npairs) { my_cost = best >> 8; my_a = (uint32_t)a; my_b = (uint32_t)b; }
+      ++npairs;  // at most S/2 <= 32
+    }
+    PTRACE(5);
+    // keep the `need` cheapest pairs
+    int rank = 0;
+    for (int m = 0; m < 32; ++m) {
+      const uint32_t cm = __shfl_sync(0xffffffffu, my_cost, m);
+      rank += (cm < my_cost || (cm == my_cost && m < lane)) ? 1 : 0;
+    }
+    const bool sel = lane < npairs && rank < need;
+    const uint32_t total = __reduce_add_sync(0xffffffffu, sel ? my_cost : 0u);
+    const bool ok = npairs >= need && total <= (uint32_t)kPairCap;
+    s_plan[lane * 2] = 255; s_plan[lane * 2 + 1] = 255;  // kPairCS == 32 columns: padding unless overwritten
+    __syncwarp();
+    if (!ok) {
+      if (lane == 0) { const int slot = atomicAdd(fcount, 1); flist[slot] = g; fbslot[g] = slot; }
+    } else {
+      if (lane == 0) fbslot[g] = -1;
+      uint32_t sel0 = 0, sel1 = 0;
+      if (sel) {
+        const uint32_t ji = s_sorted[my_a].w, jj = s_sorted[my_b].w;
+        s_plan[rank * 2] = (uint8_t)ji; s_plan[rank * 2 + 1] = (uint8_t)jj;
+        if (ji < 32) sel0 |= 1u << ji; else sel1 |= 1u << (ji - 32);
+        if (jj < 32) sel0 |= 1u << jj; else sel1 |= 1u << (jj - 32);
+      }
+      sel0 = __reduce_or_sync(0xffffffffu, sel0);
+      sel1 = __reduce_or_sync(0xffffffffu, sel1);
+      // single sites fill the remaining columns (need + (S - 2*need) == kPairCS exactly)
+      const uint32_t full0 = S >= 32 ? 0xffffffffu : ((1u << S) - 1u), full1 = S > 32 ? ((1u << (S - 32)) - 1u) : 0u;
+      const uint32_t free0 = ~sel0 & full0, free1 = ~sel1 & full1;
+      const uint32_t below = (1u << lane) - 1u;
+      if ((free0 >> lane) & 1u) { const int c = need + __popc(free0 & below); s_plan[c * 2] = (uint8_t)lane; s_plan[c * 2 + 1] = 255; }
+      if ((free1 >> lane) & 1u) { const int c = need + __popc(free0) + __popc(free1 & below); s_plan[c * 2] = (uint8_t)(lane + 32); s_plan[c * 2 + 1] = 255; }
+    }
+    __syncwarp();
+    PTRACE(6);
+    // lane c builds column c: 64 B-operand bytes (constant rows left 0 for the expander) + meta
+    const int j1 = s_plan[lane * 2], j2 = s_plan[lane * 2 + 1];
+    uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    int kind = 0;
+    if (j1 < S) { kind = 1; a0 = s_site[j1].x; a1 = s_site[j1].y; }
+    if (kind == 1 && j2 < S) { kind = 2; b0 = s_site[j2].x; b1 = s_site[j2].y; }
+    const uint32_t c0 = a0 & b0, c1 = a1 & b1;
+    const int n1 = __popc(a0) + __popc(a1), n2 = __popc(b0) + __popc(b1), nC = __popc(c0) + __popc(c1);
+    const int d1 = n1 - nC, d2 = n2 - nC;
+    const uint32_t w1 = (uint32_t)(nC + 1), w2 = w1 * (uint32_t)(d1 + 1);
+    const uint32_t tsz = kind == 2 ? w2 * (uint32_t)(d2 + 1) : 0u;
+    uint32_t incl = tsz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t2;
+    }
+    const uint32_t toff = incl - tsz;
+    // weight 1 on the common ancestors (single site: all of them), w1 / w2 on the two differences
+    const uint32_t one0 = kind == 2 ? c0 : a0, one1 = kind == 2 ? c1 : a1;
+    const uint32_t x0 = kind == 2 ? (a0 & ~c0) : 0u, x1 = kind == 2 ? (a1 & ~c1) : 0u;
+    const uint32_t y0 = kind == 2 ? (b0 & ~c0) : 0u, y1 = kind == 2 ? (b1 & ~c1) : 0u;
+    uint32_t words[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const uint32_t o = ((q < 8 ? one0 : one1) >> ((q & 7) * 4)) & 0xFu, x = ((q < 8 ? x0 : x1) >> ((q & 7) * 4)) & 0xFu,
+                     y = ((q < 8 ? y0 : y1) >> ((q & 7) * 4)) & 0xFu;
+      words[q] = ((o * 0x00204081u) & 0x01010101u) + ((x * 0x00204081u) & 0x01010101u) * w1 + ((y * 0x00204081u) & 0x01010101u) * w2;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(plan + ((size_t)g * kPairCS + lane) * kPlanColBytes);
+    dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+    dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+    dst[2] = make_uint4(words[8], words[9], words[10], words[11]);
+    dst[3] = make_uint4(words[12], words[13], words[14], words[15]);
+    // meta: kind | n1<<8 | n2<<16 | nC<<24 ; d1 | d2<<8 | toff<<16 ; table entries of the whole graph
+    const uint32_t total_g = __shfl_sync(0xffffffffu, incl, 31);
+    dst[4] = make_uint4((uint32_t)kind | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16) | ((uint32_t)nC << 24),
+                        (uint32_t)d1 | ((uint32_t)d2 << 8) | (toff << 16), total_g, 0u);
+    s_col[lane] = make_uint4((uint32_t)kind, (uint32_t)n1 | ((uint32_t)n2 << 8) | ((uint32_t)nC << 16), toff, 0u);
+  }
+  __syncthreads();
+  PTRACE(7);
+  // the pair tables of this graph, entry pc + w1*p1 + w2*p2 = V(n1, pc+p1) + V(n2, pc+p2), V(n, p) = lut[n-p][p]
+  // (the score kernel copies the block into shared memory with one bulk copy per graph); one warp per column
+  float *tg = tables + (size_t)g * kPairCap;
+  for (int c = warp; c < kPairCS; c += kPlanThreads / 32) {
+    const uint4 cm = s_col[c];
+    if (cm.x != 2u) continue;  // warp-uniform
+    const int cn1 = (int)(cm.y & 255u), cn2 = (int)((cm.y >> 8) & 255u), cnC = (int)(cm.y >> 16);
+    const int cd1 = cn1 - cnC, cd2 = cn2 - cnC, cw1 = cnC + 1;
+    float *td = tg + cm.z;
+    const float *t1 = s_tab + cn1 * (cn1 + 1) / 2, *t2 = s_tab + cn2 * (cn2 + 1) / 2;
+    for (int p2 = 0; p2 <= cd2; ++p2)
+      for (int p1 = 0; p1 <= cd1; ++p1) {
+        float *row = td + cw1 * (p1 + (cd1 + 1) * p2);
+        for (int pc = lane; pc < cw1; pc += 32) row[pc] = t1[pc + p1] + t2[pc + p2];
+      }
+  }
+  PTRACE(8);
+#undef PTRACE
 }
 
-struct Plan { int n_ntiles, tpc, n_chunks, n_items; };
-Plan make_plan(const nemb200_dataset *h, int n, int nsm) {
-  Plan pl;
-  pl.n_ntiles = (n + h->G - 1) / h->G;
-  // Items are statically strided over the CTAs, so pick the E chunking whose item count wastes the least
-  // of the last round (items are equal-sized); prefer >= 6 tiles per item to amortise the B expansion.
-  int best_chunks = 1;
-  double best_cost = 1e30;
-  for (int nc = 1; nc <= h->n_mtiles; ++nc) {
-    int tpc = (h->n_mtiles + nc - 1) / nc;
-    int chunks = (h->n_mtiles + tpc - 1) / tpc;
-    if (chunks != nc) continue;
-    long items = (long)pl.n_ntiles * chunks;
-    long rounds = (items + nsm - 1) / nsm;
-    double cost = (double)rounds * (tpc + 1.5);  // +1.5 tiles of per-item overhead
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_chunks = chunks; }
-  }
-  pl.n_chunks = best_chunks;
-  pl.tpc = (h->n_mtiles + pl.n_chunks - 1) / pl.n_chunks;
-  pl.n_chunks = (h->n_mtiles + pl.tpc - 1) / pl.tpc;
-  pl.n_items = pl.n_ntiles * pl.n_chunks;
-  return pl;
+// Sum of a graph's partial log2-likelihoods (one per CTA that worked on its N tile, see Walker) + the null term.
+// Graphs the pair planner gave up on (fbslot >= 0) take theirs from the fallback pass, whose tile count depends on
+// the device-side list length.
+__global__ void k_finalize(const double *partials, int n_slots, int G, int n_mtiles, int max_ctas, const double *sumN,
+                           int n_graphs, double *scores, const int *fbslot, const int *fcount, const double *fb_partials,
+                           int fb_G) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_graphs) return;
+  const int fs = fbslot != nullptr ? fbslot[g] : -1;
+  const double *src = partials + (size_t)g * n_slots;
+  int idx = g, tiles_g = G, n = n_graphs;
+  if (fs >= 0) { src = fb_partials + (size_t)fs * kMaxSlots; idx = fs; tiles_g = fb_G; n = *fcount; n_slots = kMaxSlots; }
+  const unsigned T = (unsigned)((n + tiles_g - 1) / tiles_g) * (unsigned)n_mtiles;
+  const int cnt = slots_of_ntile(idx / tiles_g, n_mtiles, T, effective_ctas(T, n_mtiles, max_ctas));
+  double v = 0.0;
+  for (int c = 0; c < cnt && c < n_slots; ++c) v += src[c];
+  scores[g] = *sumN + NEMB200_LN2 * v;
 }
 
 int num_sms() {
@@ -604,76 +964,134 @@ int num_sms() {
 }
 
 template <typename K>
-int launch_kernel(K kern, const Params &p, int grid, cudaStream_t st) {
-  NEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  kern<<<grid, kThreads, kSmemBytes, st>>>(p);
+int launch_kernel(K kern, const Params &p, int grid, int threads, cudaStream_t st, int smem_bytes = Lay<false>::BYTES) {
+  NEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  kern<<<grid, threads, smem_bytes, st>>>(p);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-}  // namespace
-
-size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n) {
-  Plan pl = make_plan(h, n, num_sms());
-  return 256 + sizeof(double) * (size_t)pl.n_ntiles * h->G * pl.n_chunks + 8 * 8192;  // + diagnostics time line
+// the specialised one-site table kernel for the dataset's column stride
+int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t st) {
+  // the dataset fixed the column stride: S itself for the four headline shapes, S rounded up to 8 otherwise
+  switch (h->CS == h->S ? h->S : -h->CS) {
+    case 10: return launch_kernel(k_score_tc<EPI_LUT, 10, 10>, p, grid, cta_threads(10), st);
+    case 20: return launch_kernel(k_score_tc<EPI_LUT, 20, 20>, p, grid, cta_threads(20), st);
+    case 30: return launch_kernel(k_score_tc<EPI_LUT, 30, 30>, p, grid, cta_threads(30), st);
+    case 50: return launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, cta_threads(50), st);
+    case 8: case -8: return launch_kernel(k_score_tc<EPI_LUT, 8, 8>, p, grid, cta_threads(8), st);
+    case 16: case -16: return launch_kernel(k_score_tc<EPI_LUT, 16, 16>, p, grid, cta_threads(16), st);
+    case 24: case -24: return launch_kernel(k_score_tc<EPI_LUT, 24, 24>, p, grid, cta_threads(24), st);
+    case 32: case -32: return launch_kernel(k_score_tc<EPI_LUT, 32, 32>, p, grid, cta_threads(32), st);
+    case 40: case -40: return launch_kernel(k_score_tc<EPI_LUT, 40, 40>, p, grid, cta_threads(40), st);
+    case 48: case -48: return launch_kernel(k_score_tc<EPI_LUT, 48, 48>, p, grid, cta_threads(48), st);
+    case 56: case -56: return launch_kernel(k_score_tc<EPI_LUT, 56, 56>, p, grid, cta_threads(56), st);
+    case -64: return launch_kernel(k_score_tc<EPI_LUT, 64, 64>, p, grid, cta_threads(64), st);
+    default: return launch_kernel(k_score_tc<EPI_LUT, 0, 0>, p, grid, cta_threads(0), st);
+  }
 }
 
+// workspace carve-up (bytes from the base)
+struct WsLay { size_t fcount, partials, fb_partials, plan, tables, fbslot, flist, trace, total; };
+WsLay ws_layout(const nemb200_dataset *h, int n) {
+  WsLay w;
+  size_t off = 0;
+  w.fcount = off; off += 256;
+  w.partials = off; off = align_up(off + sizeof(double) * (size_t)(n + 16) * kMaxSlots, 256);
+  w.fb_partials = off; off = align_up(off + (h->pair_ok ? sizeof(double) * (size_t)(n + 16) * kMaxSlots : 0), 256);
+  w.plan = off; off = align_up(off + (h->pair_ok ? (size_t)n * kPairCS * kPlanColBytes : 0), 256);
+  w.tables = off; off = align_up(off + (h->pair_ok ? (size_t)n * kPairCap * 4 : 0), 256);
+  w.fbslot = off; off = align_up(off + (h->pair_ok ? (size_t)n * 4 : 0), 256);
+  w.flist = off; off = align_up(off + (h->pair_ok ? (size_t)(n + 16) * 4 : 0), 256);
+  w.trace = off; off += 8 * 8192;  // diagnostics time line
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n) { return ws_layout(h, n).total; }
+
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                    int impl, cudaStream_t st) {
+                    int impl, cudaStream_t st, int leave_sms_free) {
   NEMB_REQUIRE(h->S >= 8 && h->S <= 128, "tensor-core score needs 8 <= S <= 128 (S=%d)", h->S);
+  // AUTO never picks the pair-merged kernel: its score kernel is faster (76 vs 103 us at S=50, E=10k, 1024 graphs)
+  // but the per-graph planner costs what it saves (about 20 us per 1024 graphs); callers opt in with TC_PAIR
   if (impl == NEMB200_SCORE_AUTO)
     impl = h->lut_valid ? NEMB200_SCORE_TC_LUT : (h->fixed_valid ? NEMB200_SCORE_TC_EX2 : NEMB200_SCORE_TC_EX2_2PASS);
+  NEMB_REQUIRE(impl != NEMB200_SCORE_TC_PAIR || h->pair_ok, "pair-merged table epilogue not available for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUT || h->lut_valid, "exp-table epilogue not valid for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_EX2 || h->fixed_valid, "fixed-scale ex2 epilogue not valid for this dataset");
   NEMB_REQUIRE(ws_bytes >= score_tc_workspace_bytes(h, n), "score workspace too small");
   if (n == 0) return 0;
-  const int nsm = num_sms();
-  Plan pl = make_plan(h, n, nsm);
+  // leave_sms_free: the two-group MCMC loop keeps a few SMs out of each score launch so that the other group's
+  // propose / accept / finalize kernels (and the first CTAs of its score kernel) never queue behind a full wave
+  const int nsm = num_sms() - leave_sms_free > 8 ? num_sms() - leave_sms_free : num_sms();
+  const bool pair = impl == NEMB200_SCORE_TC_PAIR;
+  const bool lut = impl == NEMB200_SCORE_TC_LUT;
+  const int G = pair ? kPairG : (lut ? h->G_lut : h->G);  // graphs per MMA N tile of the kernel that will run
+  const int CS = pair ? kPairCS : h->CS;
+  const WsLay wl = ws_layout(h, n);
+  uint8_t *wb = reinterpret_cast<uint8_t *>(ws);
+  const int n_ntiles = (n + G - 1) / G;
+  NEMB_REQUIRE((double)n_ntiles * h->n_mtiles * nsm < 4.0e9 && (double)((n + 1) / 2 + 1) * h->n_mtiles * nsm < 4.0e9,
+               "batch too large for one launch (%d graphs x %d E tiles): split it", n, h->n_mtiles);
+  const unsigned T = (unsigned)n_ntiles * (unsigned)h->n_mtiles;
   Params p;
-  p.phi = phi; p.a_img = h->a_lut; p.lut = h->lut;
-  p.partials = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(ws) + 256);
-  p.n_graphs = n; p.S = h->S; p.W = h->W; p.E = h->E; p.G = h->G;
-  p.n_ntiles = pl.n_ntiles; p.n_mtiles = h->n_mtiles; p.tpc = pl.tpc; p.n_chunks = pl.n_chunks; p.n_items = pl.n_items;
-  p.CS = h->CS;
-  p.nmma = (h->G * h->CS + 15) / 16 * 16;
-  p.ksteps = (h->S + (impl == NEMB200_SCORE_TC_LUT ? 1 : 0) + 31) / 32;
+  p.phi = phi; p.a_img = pair ? h->a_pair : h->a_lut; p.lut = h->lut;
+  p.partials = reinterpret_cast<double *>(wb + wl.partials);
+  p.n_graphs = n; p.S = h->S; p.W = h->W; p.E = h->E; p.G = G;
+  p.n_mtiles = h->n_mtiles; p.n_slots = kMaxSlots;
+  p.CS = CS;
+  p.nmma = (G * CS + 15) / 16 * 16;
+  p.ksteps = pair ? (h->S + 9 + 31) / 32 : (h->S + (lut ? 1 : 0) + 31) / 32;
   // accumulator a = 4p + 256q = 256c - 252p  ->  x = alpha2*p + beta2*q = k1*a + kc*c
   const double kappa2 = h->alpha2 - h->beta2;
   p.k1 = (float)(-kappa2 / 252.0);
   p.kc = (float)(256.0 * kappa2 / 252.0 + h->beta2);
   p.scale = impl == NEMB200_SCORE_TC_EX2_2PASS ? 0.f : (float)h->scale;
-  const int grid = pl.n_items < nsm ? pl.n_items : nsm;
+  p.plan = nullptr; p.tables = nullptr; p.glist = nullptr; p.n_dev = nullptr;
+  const int grid = effective_ctas(T, h->n_mtiles, nsm);
   int rc;
   static const char *dbg_env = getenv("NEMB200_DEBUG");
   p.debug = dbg_env ? atoi(dbg_env) : 0;
-  p.trace = (p.debug & 32) ? reinterpret_cast<long long *>(reinterpret_cast<uint8_t *>(ws) + 256 + sizeof(double) * (size_t)pl.n_ntiles * h->G * pl.n_chunks) : nullptr;
-  if (impl == NEMB200_SCORE_TC_LUT) {
-    // the dataset fixed the column stride: S itself for the four headline shapes, S rounded up to 8 otherwise
-    switch (h->CS == h->S ? h->S : -h->CS) {
-      case 10: rc = launch_kernel(k_score_tc<EPI_LUT, 10, 10>, p, grid, st); break;
-      case 20: rc = launch_kernel(k_score_tc<EPI_LUT, 20, 20>, p, grid, st); break;
-      case 30: rc = launch_kernel(k_score_tc<EPI_LUT, 30, 30>, p, grid, st); break;
-      case 50: rc = launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, st); break;
-      case 8: case -8: rc = launch_kernel(k_score_tc<EPI_LUT, 8, 8>, p, grid, st); break;
-      case 16: case -16: rc = launch_kernel(k_score_tc<EPI_LUT, 16, 16>, p, grid, st); break;
-      case 24: case -24: rc = launch_kernel(k_score_tc<EPI_LUT, 24, 24>, p, grid, st); break;
-      case 32: case -32: rc = launch_kernel(k_score_tc<EPI_LUT, 32, 32>, p, grid, st); break;
-      case 40: case -40: rc = launch_kernel(k_score_tc<EPI_LUT, 40, 40>, p, grid, st); break;
-      case 48: case -48: rc = launch_kernel(k_score_tc<EPI_LUT, 48, 48>, p, grid, st); break;
-      case 56: case -56: rc = launch_kernel(k_score_tc<EPI_LUT, 56, 56>, p, grid, st); break;
-      case -64: rc = launch_kernel(k_score_tc<EPI_LUT, 64, 64>, p, grid, st); break;
-      default: rc = launch_kernel(k_score_tc<EPI_LUT, 0, 0>, p, grid, st); break;
-    }
+  p.trace = (p.debug & 32) ? reinterpret_cast<long long *>(wb + wl.trace) : nullptr;
+  const int *fbslot = nullptr;
+  if (pair) {
+    // plan -> pair-merged kernel -> one-site kernel over the (device-side) list of graphs the planner gave up on
+    int *fcount = reinterpret_cast<int *>(wb + wl.fcount), *flist = reinterpret_cast<int *>(wb + wl.flist);
+    int *fslot = reinterpret_cast<int *>(wb + wl.fbslot);
+    uint8_t *plan = wb + wl.plan;
+    NEMB_CHECK_CUDA(cudaMemsetAsync(fcount, 0, sizeof(int), st));
+    float *tables = reinterpret_cast<float *>(wb + wl.tables);
+    k_pair_plan<<<n, kPlanThreads, 0, st>>>(phi, n, h->S, h->W, h->tabs, plan, tables, fslot, flist, fcount,
+                                         (p.debug & 64) ? reinterpret_cast<long long *>(wb + wl.trace) : nullptr);
+    NEMB_CHECK_CUDA(cudaGetLastError());
+    p.plan = plan; p.tables = tables;
+    rc = launch_kernel(k_score_tc<EPI_LUT, kPairCS, kPairCS, true>, p, grid, cta_threads(kPairCS), st, Lay<true>::BYTES);
+    if (rc) return rc;
+    Params f = p;
+    f.a_img = h->a_lut; f.plan = nullptr; f.glist = flist; f.n_dev = fcount;
+    f.partials = reinterpret_cast<double *>(wb + wl.fb_partials);
+    f.G = h->G_lut; f.CS = h->CS; f.nmma = (f.G * f.CS + 15) / 16 * 16; f.ksteps = (h->S + 1 + 31) / 32;
+    f.trace = nullptr;
+    rc = launch_lut(h, f, nsm, st);
+    fbslot = fslot;
+  } else if (lut) {
+    rc = launch_lut(h, p, grid, st);
   } else if (impl == NEMB200_SCORE_TC_EX2) {
-    rc = launch_kernel(k_score_tc<EPI_EX2, 0, 0>, p, grid, st);
+    rc = launch_kernel(k_score_tc<EPI_EX2, 0, 0>, p, grid, cta_threads(0), st);
   } else if (impl == NEMB200_SCORE_TC_EX2_2PASS) {
-    rc = launch_kernel(k_score_tc<EPI_EX2_2PASS, 0, 0>, p, grid, st);
+    rc = launch_kernel(k_score_tc<EPI_EX2_2PASS, 0, 0>, p, grid, cta_threads(0), st);
   } else {
     nemb200_set_error("unknown score impl %d", impl);
     return -1;
   }
   if (rc) return rc;
-  k_finalize<<<(n + 255) / 256, 256, 0, st>>>(p.partials, p.n_chunks, h->sumN, n, scores);
+  // 64-thread CTAs: small enough (registers) to run beside a resident score CTA of another stream (two-group MCMC loop)
+  k_finalize<<<(n + 63) / 64, 64, 0, st>>>(p.partials, p.n_slots, G, h->n_mtiles, nsm, h->sumN, n, scores, fbslot,
+                                               reinterpret_cast<const int *>(wb + wl.fcount),
+                                               reinterpret_cast<const double *>(wb + wl.fb_partials), h->G_lut);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 
 RULE_FULL, RULE_MASKED = 0, 1
-SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5}
+SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5, "pair": 6}
 
 
 def _require_cuda(device=None) -> torch.device:

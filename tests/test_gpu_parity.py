@@ -196,6 +196,37 @@ def test_score_other_error_rates_and_unsupported(nb):
         ds.score_graphs(np.zeros((1, 100, 100), dtype=np.uint8), impl="lut")   # table epilogue needs S <= 63
 
 
+@pytest.mark.parametrize("S", [33, 40, 47, 50, 52])
+def test_score_pair_merged_kernel(nb, S):
+    """Pair-merged table epilogue (two attachment sites per look-up, csrc/score_tc.cu: k_pair_plan): closed DAGs,
+    sparse and dense graphs, full orders, non-closed and cyclic digraphs.  Graphs the planner cannot pair go
+    through the one-site kernel via the device-side fallback list - both routes must agree with the witness."""
+    E = 1500
+    rng = np.random.default_rng(S)
+    _, _, D = orc.synth_dataset(S, E, seed=S)
+    A, B = orc.nem_constants(0.05, 0.1)
+    ds = nb.Dataset(D, A, B)
+    assert ds.lut_valid
+    parts = [rand_dags(rng, 40, S, p=0.3), rand_dags(rng, 40, S, p=0.05), rand_dags(rng, 20, S, p=0.6, closed=False),
+             (rng.random((30, S, S)) < 0.3).astype(np.uint8),            # arbitrary digraphs: mostly unpairable
+             np.stack([orc.order_to_graph(rng.permutation(S)) for _ in range(10)]).astype(np.uint8),
+             np.zeros((3, S, S), dtype=np.uint8), np.ones((2, S, S), dtype=np.uint8)]
+    graphs = np.concatenate(parts)
+    perm = rng.permutation(len(graphs))
+    graphs = graphs[perm]
+    w = ds.score_graphs(graphs, impl="witness")
+    got = ds.score_graphs(graphs, impl="pair")
+    assert np.allclose(got, w, rtol=REL_TC), np.abs(got / w - 1).max()
+    n_fb = int(ds._score_ws[:4].view(torch.int32).item())   # graphs that took the fallback route
+    assert (0 < n_fb or S < 47) and n_fb < len(graphs), n_fb
+    assert np.allclose(ds.score_graphs(graphs, impl="lut"), w, rtol=REL_TC)
+    ref = c_oracle.score_batch(graphs[:8], D, A, B, nthreads=4)
+    assert np.allclose(got[:8], ref, rtol=REL_TC)
+    # single graphs and ragged batch sizes (partial last tile)
+    for k in (1, 7, 9):
+        assert np.allclose(ds.score_graphs(graphs[:k], impl="pair"), w[:k], rtol=REL_TC)
+
+
 def test_score_full_size_c3_lut_vs_witness(nb):
     """BASELINE config 3 shape (S=50, E=10k, 1024 graphs): tensor-core path vs the fp64 witness kernel
     on the device, plus permutation invariance of the batch order."""
@@ -207,7 +238,7 @@ def test_score_full_size_c3_lut_vs_witness(nb):
     orders = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
     bits = ds.order_graphs(orders)
     w = ds.score_bits(bits, impl="witness").cpu().numpy()
-    for impl in TC_IMPLS:
+    for impl in TC_IMPLS + ["pair"]:
         got = ds.score_bits(bits, impl=impl).cpu().numpy()
         assert np.allclose(got, w, rtol=REL_TC), impl
     perm = torch.from_numpy(rng.permutation(n)).to(bits.device)
@@ -309,6 +340,23 @@ def test_mcmc_trajectory_vs_oracle(nb, S, E, rule, use_nem, impl):
         total += ref["edge_counts"]
     assert np.array_equal(res.edge_counts, total)
     assert 0 < res.accept_counts.sum() < n_chains * n_iter
+
+
+def test_mcmc_with_pair_merged_score(nb):
+    """The device loop with the pair-merged score kernel (impl="pair") reproduces the oracle chain draw for draw."""
+    S, E = 40, 200
+    _, _, D = orc.synth_dataset(S, E, seed=7)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rng = np.random.default_rng(1)
+    cand = (rng.random((S, S)) < 0.4).astype(np.uint8)
+    orders0 = np.stack([rng.permutation(S) for _ in range(5)]).astype(np.int32)
+    ds = nb.Dataset(D, A, B)
+    res = ds.run_chains(orders0, 300, 2.0 * S / E, swap_prob=0.9, seed=99, chain_offset=3, rule=1, cand=cand, use_nem=True,
+                        burn_in=50, impl="pair").result()
+    for c in range(5):
+        ref = c_oracle.mcmc_chain(D, A, B, orders0[c], 300, 2.0 * S / E, swap_prob=0.9, seed=99, chain=3 + c, rule=1,
+                                  cand=cand, use_nem=True, burn_in=50)
+        _compare_chain(res, c, ref, S)
 
 
 @pytest.mark.parametrize("impl", ["fused", "lut"])

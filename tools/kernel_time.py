@@ -9,6 +9,8 @@ if os.environ.get('ZEROD'): D = D * 0
 if os.environ.get('RANDD'): D = (np.random.default_rng(0).random(D.shape) < 0.5).astype(np.uint8)
 ds = nb.Dataset(D, *nb.synth.nem_constants(0.05, 0.1), sort_egenes=os.environ.get('SORT','1')=='1')
 bits = ds.order_graphs(nb.synth.random_orders(n, S, 1), rule=1, cand=(np.random.default_rng(0).random((S, S)) < 0.3).astype(np.uint8))
+if os.environ.get('GRAPHS') == 'empty': bits.zero_()
+if os.environ.get('GRAPHS') == 'full': bits = ds.order_graphs(nb.synth.random_orders(n, S, 1))
 impl = sys.argv[4] if len(sys.argv) > 4 else "auto"
 for _ in range(5): ds.score_bits(bits, impl=impl)
 torch.cuda.synchronize()
