@@ -92,6 +92,19 @@ size_t nemb200_cell_ll_workspace_bytes(int E);
 int nemb200_cell_ll(const double *d_cell, int rows, int E, double *d_order_weights, double *d_ll,
                     void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- per-order edge-weight fit: replaces the loop of one-dimensional scipy fits in
+ *      NEMOrderMCMC.get_optimal_weights (nem_order_mcmc.py:183-194) with calculate_local_optimum (:160-170) and
+ *      the objective local_ll_sum_penalized (:18-23).  All matrices are S x S float64 row-major, [i][k] = node i,
+ *      parent k.  d_weights: current parent weights (raw, the kernel applies expit as :163 does);
+ *      d_order_weights: (S+1) x E posterior attachment weights from nemb200_cell_ll (:89-93); d_ancestor_x: the
+ *      clipped (I - expit(W))^-1 - I of :185; d_mask: uint8, 1 = fit this pair (permissible parents, or only those
+ *      touching the swapped nodes as in :190-194), 0 = copy the weight through.  d_out_weights[i][k] = the
+ *      minimiser of the objective in s = expit(x) over [0,1] (what the reference thresholds at 0.5, :212).  The
+ *      reference stops L-BFGS-B at tol=0.01; this returns the exact global minimiser. */
+int nemb200_fit_edges(const nemb200_dataset *h, const double *d_weights, const double *d_order_weights,
+                      const double *d_ancestor_x, const uint8_t *d_mask, double *d_out_weights,
+                      void *stream);
+
 /* ---- order -> graph: replaces get_permissible_parents (nem_order_mcmc.py:54-77) +
  *      create_dag / create_nem (:210-221) with the deterministic rules of DESIGN.md
  *      (FULL: every earlier node is a parent; MASKED: & d_cand_bits, S x W words shared by all

@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
     L.nemb200_cell_ll_workspace_bytes.argtypes = [i32]
     L.nemb200_cell_ll.argtypes = [vp, i32, i32, vp, vp, vp, sz, vp]
     L.nemb200_synth_knockdown.argtypes = [vp, vp, i32, i32, dbl, dbl, u64, vp, vp, vp]
+    L.nemb200_fit_edges.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -79,7 +80,7 @@ EXPORTS = ["nemb200_version", "nemb200_last_error", "nemb200_dataset_bytes", "ne
            "nemb200_score_workspace_bytes", "nemb200_score_batch", "nemb200_order_to_graph",
            "nemb200_mcmc_workspace_bytes", "nemb200_mcmc_run", "nemb200_replica_exchange",
            "nemb200_edge_counts_reduce", "nemb200_cell_ratios", "nemb200_cell_ll_workspace_bytes",
-           "nemb200_cell_ll", "nemb200_synth_knockdown"]
+           "nemb200_cell_ll", "nemb200_synth_knockdown", "nemb200_fit_edges"]
 
 
 def check(rc: int) -> None:

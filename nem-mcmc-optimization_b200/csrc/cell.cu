@@ -128,3 +128,107 @@ extern "C" int nemb200_synth_knockdown(const uint32_t *d_adj_bits, const int32_t
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- per-order edge-weight fit: the S(S-1)/2 one-dimensional fits of
+//      NEMOrderMCMC.get_optimal_weights / calculate_local_optimum (nem_order_mcmc.py:160-208) as one launch.
+//      One CTA per (child i, parent k) pair.  c[e] follows :161-164 (two-valued exp(T[k,e]), posterior attachment
+//      weight of site k, expit of the current weight); the objective is local_ll_sum_penalized (:18-23) in the
+//      variable s = expit(x) that the reference thresholds:
+//          G(s) = -sum_e log(1 + c_e s) + |s - anc| + s (1 - s),        G'(s) = -H(s) + sign(s - anc) + 1 - 2 s,
+//      H(s) = sum_e c_e / (1 + c_e s).  The reference runs scipy's L-BFGS-B stopped at tol = 0.01 (its result is not a
+//      function of the inputs alone); this kernel returns the global minimiser over s in [0, 1]: end points, the kink
+//      at anc and every stationary point bracketed by kFitGrid probes per side and refined by kFitBisect bisection
+//      steps (the tests' CPU restatement runs the same procedure with the same constants).
+namespace {
+constexpr int kFitThreads = 256;
+constexpr int kFitGrid = 16;
+constexpr int kFitBisect = 40;
+
+struct FitCtx {
+  const uint32_t *dcol;
+  const double *ow_k;  // posterior attachment weights of site k, E doubles
+  int W, E, k;
+  double w, u1, u0;    // expit(current weight), exp(-A) - 1, exp(B) - 1
+  double *red;         // kFitThreads doubles of shared memory
+};
+
+// mode 0: H(s) = sum c/(1+cs);  mode 1: sum log(1+cs).  Every thread returns the block-wide sum (fixed tree: deterministic).
+__device__ double fit_sum(const FitCtx &f, double s, int mode) {
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < f.E; e += kFitThreads) {
+    const uint32_t d = (f.dcol[(size_t)e * f.W + (f.k >> 5)] >> (f.k & 31)) & 1u;
+    const double u = d ? f.u1 : f.u0;
+    const double a = u * f.ow_k[e];
+    const double b = 1.0 - f.w * a + f.w * u;
+    const double c = a / b;
+    acc += mode == 0 ? c / (1.0 + c * s) : log(1.0 + c * s);
+  }
+  __syncthreads();  // red may still be read by the previous call
+  f.red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kFitThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) f.red[threadIdx.x] += f.red[threadIdx.x + o];
+    __syncthreads();
+  }
+  return f.red[0];
+}
+
+__global__ void __launch_bounds__(kFitThreads) k_fit_edges(const uint32_t *__restrict__ dcol, int S, int W, int E, double A,
+                                                           double B, const double *__restrict__ weights,
+                                                           const double *__restrict__ ow, const double *__restrict__ anc_x,
+                                                           const uint8_t *__restrict__ mask, double *__restrict__ out) {
+  __shared__ double red[kFitThreads];
+  const int pr = blockIdx.x, k = pr % S;
+  if (!mask[pr]) {
+    if (threadIdx.x == 0) out[pr] = weights[pr];
+    return;
+  }
+  FitCtx f;
+  f.dcol = dcol; f.ow_k = ow + (size_t)k * E; f.W = W; f.E = E; f.k = k;
+  f.w = 1.0 / (1.0 + exp(-weights[pr]));
+  f.u1 = exp(-A) - 1.0; f.u0 = exp(B) - 1.0;
+  f.red = red;
+  const double xa = anc_x[pr];
+  const double anc = fmin(fmax(xa, 0.0), 1.0);
+  // candidates in ascending order of s; ties keep the smaller s (strict < below)
+  double cand[3 + 2 * kFitGrid];
+  int nc = 0;
+  cand[nc++] = 0.0;
+  for (int side = 0; side < 2; ++side) {
+    const double lo_end = side == 0 ? 0.0 : anc, hi_end = side == 0 ? anc : 1.0, sg = side == 0 ? -1.0 : 1.0;
+    if (side == 1) cand[nc++] = anc;
+    if (!(hi_end > lo_end)) continue;
+    double prev_s = lo_end, prev_d = -fit_sum(f, lo_end, 0) + sg + 1.0 - 2.0 * lo_end;
+    for (int g = 1; g <= kFitGrid; ++g) {
+      const double s = lo_end + (hi_end - lo_end) * (double)g / (double)kFitGrid;
+      const double d = -fit_sum(f, s, 0) + sg + 1.0 - 2.0 * s;
+      if (prev_d < 0.0 && 0.0 <= d) {
+        double lo = prev_s, hi = s;
+        for (int it = 0; it < kFitBisect; ++it) {
+          const double mid = 0.5 * (lo + hi);
+          if (-fit_sum(f, mid, 0) + sg + 1.0 - 2.0 * mid < 0.0) lo = mid; else hi = mid;
+        }
+        cand[nc++] = 0.5 * (lo + hi);
+      }
+      prev_s = s; prev_d = d;
+    }
+  }
+  cand[nc++] = 1.0;
+  double best_s = 0.0, best_g = 0.0;
+  for (int q = 0; q < nc; ++q) {
+    const double s = cand[q];
+    const double g = -fit_sum(f, s, 1) + fabs(s - xa) + s * (1.0 - s);
+    if (q == 0 || g < best_g) { best_s = s; best_g = g; }
+  }
+  if (threadIdx.x == 0) out[pr] = best_s;
+}
+}  // namespace
+
+extern "C" int nemb200_fit_edges(const nemb200_dataset *h, const double *d_weights, const double *d_order_weights,
+                                 const double *d_ancestor_x, const uint8_t *d_mask, double *d_out_weights, void *stream) {
+  NEMB_REQUIRE(h && d_weights && d_order_weights && d_ancestor_x && d_mask && d_out_weights, "null argument");
+  k_fit_edges<<<h->S * h->S, kFitThreads, 0, (cudaStream_t)stream>>>(h->dcol, h->S, h->W, h->E, h->A, h->B, d_weights,
+                                                                    d_order_weights, d_ancestor_x, d_mask, d_out_weights);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -3,9 +3,11 @@ with the same call surface (nem_order_mcmc.py:29, 257, 344).  The loop of ``meth
 as a device-resident multi-chain MCMC (engine.ChainState / nemb200_mcmc_run).
 
 Differences, all documented in DESIGN.md:
-  * the per-order L-BFGS-B edge-weight fit (get_optimal_weights :172-208, 97 % of the reference's time
-    and not reproducible across scipy versions) is replaced by a deterministic order->graph rule
-    (``rule='full'`` or ``rule='masked'`` with a candidate-edge matrix) - SURVEY 8 a8;
+  * inside the device loop of ``method`` the per-order L-BFGS-B edge-weight fit (get_optimal_weights :172-208,
+    97 % of the reference's time and not reproducible across scipy versions) is replaced by a deterministic
+    order->graph rule (``rule='full'`` or ``rule='masked'`` with a candidate-edge matrix) - SURVEY 8 a8; the fit
+    itself is available as a batched GPU operator (``fit_weights`` / ``get_optimal_weights``) that
+    returns the exact minimiser of the reference's objective;
   * the score is the clean (no expit) NEM score nem.py:72-86 (SURVEY Q6);
   * randomness is counter-based Philox keyed by ``seed`` (the reference ignores ``seed``, Q4);
   * ``opt_weights`` (raises NameError at HEAD, Q1) does not exist.
@@ -97,6 +99,84 @@ class NEMOrderMCMC:
         """nem_order_mcmc.py:216-221 (closure on the GPU)."""
         nem_weights = utils.ancestor(1 * (np.asarray(weights) > 0.5))
         return nem_weights.T, nem_weights
+
+    # ---- per-order edge-weight fit (SURVEY 8 f-1) -------------------------------------------------------
+    def expit_parent_weights(self, weights):
+        """nem_order_mcmc.py:152-157: expit on the entries of permissible parents only."""
+        w = np.array(weights, dtype=np.float64, copy=True)
+        for i in range(self.num_s):
+            for j in self.parents_list[i]:
+                w[i][j] = 1.0 / (1.0 + np.exp(-w[i][j]))
+        return w
+
+    def fit_weights(self, weights=None, pairs=None):
+        """One pass of the S(S-1)/2 one-dimensional edge fits of get_optimal_weights (:181-194) on the GPU
+        (nemb200_cell_ratios + nemb200_cell_ll + nemb200_fit_edges): every pair in `pairs` (default: all
+        permissible (node, parent) pairs) gets the minimiser of local_ll_sum_penalized (:18-23), all computed from
+        the current weights.  Returns (new weights, soft log-likelihood of the current weights).  The reference stops
+        scipy's L-BFGS-B at tol=0.01; this is the exact minimiser of the same objective."""
+        S, E = self.num_s, self.num_e
+        dev = self.nem.device
+        W = np.asarray(self.parent_weights if weights is None else weights, dtype=np.float64)
+        perm = np.zeros((S, S), dtype=np.uint8)
+        for i in range(S):
+            for j in self.parents_list[i]:
+                perm[i][j] = 1
+        mask = perm if pairs is None else (perm & (np.asarray(pairs) != 0)).astype(np.uint8)
+        L = _lib.lib()
+        st = torch.cuda.current_stream(dev)
+        # soft cell ratios of the current weights with the driver's expit (:79-87) and the posterior (:89-93)
+        wsoft = np.where(perm != 0, np.where(W != 0, W, 1e-300), 0.0)
+        wt = torch.from_numpy(np.ascontiguousarray(wsoft)).to(dev)
+        cell = torch.empty((S + 1, E), dtype=torch.float64, device=dev)
+        _lib.check(L.nemb200_cell_ratios(self.nem.dataset._h, engine._ptr(wt), 1, engine._ptr(cell), engine._stream_ptr(st)))
+        ws = torch.empty(max(L.nemb200_cell_ll_workspace_bytes(E), 8), dtype=torch.uint8, device=dev)
+        ll = torch.empty(1, dtype=torch.float64, device=dev)
+        ow = torch.empty_like(cell)
+        _lib.check(L.nemb200_cell_ll(engine._ptr(cell), S + 1, E, engine._ptr(ow), engine._ptr(ll), engine._ptr(ws),
+                                     ws.numel(), engine._stream_ptr(st)))
+        # ancestor_x (:185): clip((I - expit(W))^-1 - I, 0, 1), an S x S inverse on the device
+        wexp = torch.from_numpy(self.expit_parent_weights(W)).to(dev)
+        eye = torch.eye(S, dtype=torch.float64, device=dev)
+        anc = torch.clamp(torch.linalg.inv(eye - wexp) - eye, 0.0, 1.0).contiguous()
+        wraw = torch.from_numpy(np.ascontiguousarray(W)).to(dev)
+        mk = torch.from_numpy(np.ascontiguousarray(mask)).to(dev)
+        out = torch.empty((S, S), dtype=torch.float64, device=dev)
+        _lib.check(L.nemb200_fit_edges(self.nem.dataset._h, engine._ptr(wraw), engine._ptr(ow), engine._ptr(anc),
+                                       engine._ptr(mk), engine._ptr(out), engine._stream_ptr(st)))
+        self.ancestor_x = anc.cpu().numpy()
+        self.order_weights = ow  # device tensor (S+1, E)
+        return out.cpu().numpy(), float(ll.item())
+
+    def calculate_local_optimum(self, i, k):
+        """nem_order_mcmc.py:160-170 for one pair (the batched form is fit_weights)."""
+        pairs = np.zeros((self.num_s, self.num_s), dtype=np.uint8)
+        pairs[i][k] = 1
+        return float(self.fit_weights(pairs=pairs)[0][i][k])
+
+    def get_optimal_weights(self, abs_diff=1e-6, max_iter=1, use_nem=False, i1=None, i2=None, init=False,
+                            ultra_verbose=False):
+        """nem_order_mcmc.py:172-208: up to max_iter passes of the per-edge fits (all permissible pairs if init, else
+        only the pairs touching nodes i1 / i2, :190-194), then threshold (create_dag / create_nem) and return the
+        log-likelihood of the thresholded graph through the same expit-on-weights cell ratios as :207."""
+        old_ll, ll_diff, iter_count = -float("inf"), float("inf"), 1
+        self.ll = 0.0
+        S = self.num_s
+        while iter_count <= max_iter and ll_diff > abs_diff:
+            pairs = None
+            if not init:
+                pairs = np.zeros((S, S), dtype=np.uint8)
+                for n_ in (i1, i2):
+                    if n_ is not None:
+                        pairs[n_, :] = 1
+                        pairs[:, n_] = 1
+            new_w, self.ll = self.fit_weights(pairs=pairs)
+            ll_diff = abs(self.ll - old_ll)
+            old_ll = self.ll
+            iter_count += 1
+            self.parent_weights = new_w
+        _, dag_weights = self.create_nem(self.parent_weights) if use_nem else self.create_dag(self.parent_weights)
+        return utils.compute_ll(self.compute_cell_ratios(dag_weights))
 
     # ---- proposal / acceptance as host-callable units (same semantics as the device kernels) ---------
     def accepting(self, score, curr_score, gamma, net, curr_net, perm_order, curr_perm_order):

@@ -377,3 +377,121 @@ def philox_observed(adj, end_nodes, alpha, beta, seed):
             elif real[i, e] == 1 and u < beta:
                 obs[i, e] = 0
     return real, obs
+
+
+# --------------------------------------------------------------------------
+# per-order edge-weight fit: nem_order_mcmc.py:172-208
+# --------------------------------------------------------------------------
+# Parity status: PINNED ONLY WITHIN ONE SCIPY VERSION.  tests/golden/fit.npz holds reference runs made in this
+# container (scipy version stored in the file); ``fit_pass(minimiser="lbfgsb")`` reproduces them.  The reference
+# stops scipy's L-BFGS-B at tol=0.01, so its iterates are not a mathematical function of the inputs;
+# ``minimiser="exact"`` returns the true minimiser of the same objective (what the CUDA path computes) and the tests
+# state how far the two are apart (thresholded DAGs).
+
+
+def _expit(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def fit_objective(x, c, x_ancestor):
+    """local_ll_sum_penalized, nem_order_mcmc.py:18-23."""
+    ex_x = _expit(x)
+    return -np.sum(np.log(c * ex_x + 1.0)) + np.abs(ex_x - x_ancestor) + ex_x * (1.0 - ex_x)
+
+
+def fit_inputs(D, A, B, order, W):
+    """Everything get_optimal_weights computes before the per-edge fits (nem_order_mcmc.py:181-185):
+    parents (:63-64), soft cell ratios with expit on the weights (:79-87), posterior attachment weights
+    (:89-93) and ancestor_x (:185 with expit_parent_weights :152-157)."""
+    D = np.asarray(D)
+    s, _ = D.shape
+    T, _, U = score_tables(D, A, B)
+    order = np.asarray(order)
+    pos = np.empty(s, dtype=np.int64)
+    pos[order] = np.arange(s)
+    perm = pos[None, :] < pos[:, None]                  # perm[i][k]: k is a permissible parent of i
+    W = np.asarray(W, dtype=np.float64)
+    cell = U.copy()
+    for i in range(s):
+        for k in order[:pos[i]]:
+            w = _expit(W[i][k])
+            cell[i] += np.log(1.0 - w + w * np.exp(T[k]))
+    cs = np.logaddexp.reduce(cell, axis=0)
+    ow = np.exp(cell - cs)
+    Wexp = np.where(perm, _expit(W), W)
+    anc_x = np.clip(np.linalg.inv(np.identity(s) - Wexp) - np.identity(s), 0, 1)
+    return T, perm, ow, anc_x, float(np.sum(cs))
+
+
+def fit_c(T, ow, W, i, k):
+    """The per-E-gene coefficient of calculate_local_optimum, nem_order_mcmc.py:161-164."""
+    local_vec = np.exp(T[k])
+    a = (local_vec - 1.0) * ow[k]
+    w = _expit(W[i][k])
+    b = 1.0 - w * a + w * (local_vec - 1.0)
+    return a / b
+
+
+FIT_GRID = 16    # probe points per side of the kink when bracketing stationary points
+FIT_BISECT = 40  # bisection steps per bracket
+
+
+def fit_minimise_exact(c, x_ancestor):
+    """Global argmin over s = expit(x) in [0, 1] of
+        G(s) = -sum log(1 + c s) + |s - anc| + s (1 - s)
+    (the objective of :18-23 in the variable the reference thresholds).  G is smooth on both sides of the kink at
+    anc; with few / weak E-genes the concave s(1-s) term can dominate, so the minimum is searched among the end
+    points, the kink and every stationary point where G' = -H(s) + sign(s - anc) + 1 - 2s, H(s) = sum c/(1 + c s),
+    changes sign from - to + between neighbouring probe points (FIT_GRID per side, refined by bisection).  Ties go
+    to the smallest s.  The CUDA kernel k_fit_edges runs the same procedure with the same constants."""
+    c = np.asarray(c, dtype=np.float64)
+    anc = float(min(max(x_ancestor, 0.0), 1.0))
+    H = lambda s: float(np.sum(c / (1.0 + c * s)))
+    G = lambda s: float(-np.sum(np.log(1.0 + c * s)) + abs(s - x_ancestor) + s * (1.0 - s))
+    cands = [0.0, 1.0, anc]
+    for lo_end, hi_end, sg in ((0.0, anc, -1.0), (anc, 1.0, 1.0)):
+        if hi_end <= lo_end:
+            continue
+        dG = lambda s: -H(s) + sg + 1.0 - 2.0 * s
+        prev_s, prev_d = lo_end, dG(lo_end)
+        for g in range(1, FIT_GRID + 1):
+            s = lo_end + (hi_end - lo_end) * g / FIT_GRID
+            d = dG(s)
+            if prev_d < 0.0 <= d:
+                lo, hi = prev_s, s
+                for _ in range(FIT_BISECT):
+                    mid = 0.5 * (lo + hi)
+                    if dG(mid) < 0.0:
+                        lo = mid
+                    else:
+                        hi = mid
+                cands.append(0.5 * (lo + hi))
+            prev_s, prev_d = s, d
+    best_s, best_g = None, None
+    for s in sorted(cands):
+        g = G(s)
+        if best_g is None or g < best_g:
+            best_s, best_g = s, g
+    return best_s
+
+
+def fit_pass(D, A, B, order, W, minimiser="exact"):
+    """One pass of get_optimal_weights(init=True, max_iter=1), nem_order_mcmc.py:172-208: every permissible pair gets
+    the minimiser of its 1-D objective, all computed from the OLD weights (:183-189).  minimiser="lbfgsb" calls scipy
+    exactly as :167 does; "exact" is the true minimiser.  Returns (new weights, soft log-likelihood of the old ones)."""
+    s = np.asarray(D).shape[0]
+    T, perm, ow, anc_x, ll = fit_inputs(D, A, B, order, W)
+    new = np.array(W, dtype=np.float64, copy=True)
+    for i in range(s):
+        for k in range(s):
+            if not perm[i][k]:
+                continue
+            c = fit_c(T, ow, W, i, k)
+            if minimiser == "lbfgsb":
+                from scipy.optimize import minimize
+                res = minimize(fit_objective, x0=_expit(W[i][k]), bounds=[(-float("inf"), float("inf"))],
+                               args=(c, anc_x[i][k]), method="L-BFGS-B", tol=0.01)
+                new[i][k] = float(_expit(res.x[0]))
+            else:
+                new[i][k] = fit_minimise_exact(c, anc_x[i][k])
+    return new, ll

@@ -610,3 +610,50 @@ def test_replica_exchange_swap_rate(nb):
     expect = sum(min(1.0, np.exp(-((g[i] - g[i + 1]) * (s[i + 1] - s[i])))) for i in range(0, n, 2))
     got = int(st2.replica_exchange(ladder, 0, 0).item())
     assert abs(got - expect) <= max(6.0, 4 * np.sqrt(expect))
+
+
+# ---------------------------------------------------------------------------- per-order weight fit (f-1)
+def test_fit_edges_vs_exact_oracle(nb):
+    """nemb200_fit_edges (one CTA per (node, parent) pair) against oracle.fit_pass(minimiser="exact") on the
+    reference's golden fit inputs: same minimisers, same thresholded DAG, same soft log-likelihood."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "fit.npz"))
+
+    class _Nem:  # the attributes NEMOrderMCMC reads
+        pass
+    for tag in [str(t) for t in z["cases"]]:
+        D, (A, B), order = z[f"D_{tag}"], z[f"AB_{tag}"], z[f"order_{tag}"]
+        S, E = D.shape
+        nm = _Nem()
+        nm.num_s, nm.num_e = S, E
+        nm.dataset = nb.Dataset(D, float(A), float(B))
+        nm.device = nm.dataset.device
+        _, _, U = orc.score_tables(D, A, B)
+        nm.U = U
+        mc = nb.NEMOrderMCMC(nm, order)
+        for w_in in (z[f"w0_{tag}"], z[f"w1_{tag}"]):
+            mc.get_permissible_parents(order, init=True)
+            mc.parent_weights = np.array(w_in, copy=True)
+            got, ll = mc.fit_weights()
+            ref, ll_ref = orc.fit_pass(D, A, B, order, w_in, "exact")
+            assert ll == pytest.approx(ll_ref, rel=1e-11)
+            perm = w_in != 0
+            close = np.abs(got - ref)[perm] < 1e-6
+            assert close.mean() >= 0.98, (tag, close.mean())       # ties between equal minima may pick the other one
+            decided = np.abs(ref - 0.5) > 1e-6
+            assert np.array_equal((got > 0.5)[perm & decided & (np.abs(got - ref) < 1e-6)],
+                                  (ref > 0.5)[perm & decided & (np.abs(got - ref) < 1e-6)])
+            assert np.array_equal(got[~perm], w_in[~perm])          # masked-out pairs are copied through
+        # the drop-in method: one pass + threshold + score, as the reference's driver calls it (:277)
+        mc.get_permissible_parents(order, init=True)
+        dag_ll = mc.get_optimal_weights(init=True, use_nem=False)
+        ref_w, _ = orc.fit_pass(D, A, B, order, z[f"w0_{tag}"], "exact")
+        dagw = 1 * (ref_w > 0.5)
+        T, _, U = orc.score_tables(D, A, B)
+        cell = U.copy()
+        ex = 1.0 / (1.0 + np.exp(-dagw.astype(float)))
+        pos = np.empty(S, dtype=int); pos[order] = np.arange(S)
+        for i in range(S):
+            for k in order[:pos[i]]:
+                cell[i] += np.log(1.0 - ex[i][k] + ex[i][k] * np.exp(T[k]))     # :79-87 with the expit quirk
+        assert dag_ll == pytest.approx(float(np.logaddexp.reduce(cell, axis=0).sum()), rel=1e-10)
