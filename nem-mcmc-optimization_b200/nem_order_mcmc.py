@@ -205,6 +205,8 @@ class NEMOrderMCMC:
         """nem_order_mcmc.py:257-310 -> (best_score, best_dag) with best_dag[j][i]=1 iff edge j->i.
         n_chains independent chains run at once (chain 0 starts from self.perm_order); the best over
         all chains is returned and `edge_freq` holds the posterior edge frequencies."""
+        if rule == "fit":
+            return self._method_fit(swap_prob, gamma, seed, n_iterations, verbose, use_nem)
         ds = self.nem.dataset
         orders0 = start_orders(self.perm_order, n_chains, seed)
         gam = np.broadcast_to(np.asarray(gamma, dtype=np.float64), (n_chains,))
@@ -241,6 +243,47 @@ class NEMOrderMCMC:
             acc = res.accept_counts.sum() / max(1, n_iterations * n_chains)
             print(f"order-MCMC: {n_chains} chain(s) x {n_iterations} iterations, acceptance {acc:.3f}, "
                   f"best score {self.best_score:.6f} (chain {k})")
+        return self.best_score, self.best_dag
+
+    def _method_fit(self, swap_prob, gamma, seed, n_iterations, verbose, use_nem):
+        """The reference's own loop (nem_order_mcmc.py:257-310) with its order->DAG step: every iteration proposes
+        an order (:275), resets the weights (:276), fits all permissible edge weights on the GPU
+        (get_optimal_weights, :277), thresholds them into a DAG / NEM (:283-286) and accepts with :224-229.  One
+        chain, host-driven (a handful of launches and one host sync per iteration) - the reference-faithful mode;
+        the device-resident multi-chain loop is `rule="full"/"masked"`.  `seed` seeds Python's `random` (the
+        reference ignores it)."""
+        random.seed(seed)
+        curr_score = self.get_optimal_weights(init=True, use_nem=use_nem)  # :258, from the constructor's weights (1.0)
+        best_score = curr_score
+        best_dag, _ = self.create_dag(self.parent_weights)
+        curr_perm_order = np.array(self.perm_order)
+        best_order = curr_perm_order
+        curr_dag = np.zeros((self.num_s, self.num_s))
+        curr_score_list, best_score_list, all_score_list = [curr_score], [best_score], [curr_score]
+        best_parents_list = self.parents_list.copy()
+        n_acc = 0
+        for _ in range(n_iterations):
+            perm_order, _, _ = self.get_new_order(curr_perm_order, swap_prob=swap_prob)
+            self.reset(perm_order, init=True)
+            ll = self.get_optimal_weights(init=True, use_nem=use_nem)
+            all_score_list.append(ll)
+            dag, _ = self.create_nem(self.parent_weights) if use_nem else self.create_dag(self.parent_weights)
+            curr_score_list.append(curr_score)
+            acc, curr_score, curr_dag, curr_perm_order = self.accepting(ll, curr_score, gamma, dag, curr_dag, perm_order,
+                                                                         curr_perm_order)
+            if acc:
+                n_acc += 1
+                if curr_score > best_score:
+                    best_score, best_dag, best_order = curr_score, dag, np.array(curr_perm_order)
+                    best_parents_list = self.parents_list.copy()
+                    best_score_list.append(best_score)
+        self.best_score, self.best_dag, self.best_order = best_score, np.asarray(best_dag).astype(int), best_order
+        self.all_score_list, self.curr_score_list, self.best_score_list = all_score_list, curr_score_list, best_score_list
+        self.parents_list = best_parents_list
+        self.accept_counts = np.array([n_acc])
+        if verbose:
+            print(f"order-MCMC (fitted edge weights): {n_iterations} iterations, acceptance "
+                  f"{n_acc / max(1, n_iterations):.3f}, best score {best_score:.6f}")
         return self.best_score, self.best_dag
 
     def condition(self, i, j):

@@ -657,3 +657,21 @@ def test_fit_edges_vs_exact_oracle(nb):
             for k in order[:pos[i]]:
                 cell[i] += np.log(1.0 - ex[i][k] + ex[i][k] * np.exp(T[k]))     # :79-87 with the expit quirk
         assert dag_ll == pytest.approx(float(np.logaddexp.reduce(cell, axis=0).sum()), rel=1e-10)
+
+
+def test_mcmc_method_with_fitted_weights(nb):
+    """The reference's own smoke test (tests/utils.tests.py:30-49: 5-node DAG, E=8, errors (0.05, 0.1), order
+    [4,3,2,1,0], 110 iterations, gamma = 2S/E, no assertion upstream) through method(rule="fit"): the reference-
+    faithful loop with the GPU edge-weight fit.  Checks the bookkeeping contract of :303-309."""
+    adj = np.array([[0, 1, 1, 1, 1], [0, 0, 1, 1, 1], [0, 0, 0, 1, 1], [0, 0, 0, 0, 1], [0, 0, 0, 0, 0]])
+    end_nodes = np.array([0, 1, 2, 3, 4, 0, 1, 2])
+    model = nb.NEM(adj, end_nodes, (0.05, 0.1), 5, 8, seed=42)
+    mc = nb.NEMOrderMCMC(model, np.array([4, 3, 2, 1, 0]))
+    best_score, best_dag = mc.method(n_iterations=110, gamma=2 * 5 / 8, seed=42, verbose=False, rule="fit")
+    assert best_dag.shape == (5, 5) and set(np.unique(best_dag)) <= {0, 1}
+    assert len(mc.all_score_list) == 111 and len(mc.curr_score_list) == 111
+    assert best_score == max(mc.best_score_list) and best_score >= mc.all_score_list[0]
+    assert sorted(mc.best_order.tolist()) == [0, 1, 2, 3, 4]
+    pos = np.empty(5, dtype=int); pos[mc.best_order] = np.arange(5)
+    a, b = np.nonzero(best_dag)
+    assert np.all(pos[a] < pos[b])           # only order-compatible edges (SURVEY Q7 fixed)
