@@ -140,6 +140,41 @@ def small_mcmc_configs(nb, synth, with_cpu):
     return res
 
 
+def edge_fit_leg(nb, synth, with_cpu):
+    """one pass of the per-order edge-weight fit (get_optimal_weights, nem_order_mcmc.py:172-208) at
+    S=20 x E=1000 (190 one-dimensional fits): GPU operator vs the scipy L-BFGS-B restatement on one host core."""
+    import torch
+    s, e = 20, 1000
+    _, _, D = synth.dataset(s, e, seed=0, alpha=ALPHA, beta=BETA)
+    A, B = synth.nem_constants(ALPHA, BETA)
+
+    class _Nem:
+        pass
+    nm = _Nem()
+    nm.num_s, nm.num_e = s, e
+    nm.dataset = nb.Dataset(D, A, B)
+    nm.device = nm.dataset.device
+    nm.U = np.zeros((s + 1, e))
+    order = np.random.default_rng(3).permutation(s)
+    mc = nb.NEMOrderMCMC(nm, order)
+    mc.get_permissible_parents(order, init=True)
+    mc.fit_weights()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        mc.fit_weights()
+    torch.cuda.synchronize()
+    row = {"config": "S=20 E=1000, one pass = 190 edge fits", "gpu_ms_per_pass": (time.perf_counter() - t0) / reps * 1e3,
+           "semantics": "exact minimiser of nem_order_mcmc.py:18-23 per edge (reference: scipy L-BFGS-B stopped at tol=0.01)"}
+    if with_cpu:
+        from oracle import nem_oracle as orc
+        t0 = time.perf_counter()
+        orc.fit_pass(D, A, B, order, mc.parent_weights, "lbfgsb")
+        row["cpu_scipy_port_one_core_ms_per_pass"] = (time.perf_counter() - t0) * 1e3
+    return row
+
+
 def config5_sweep(nb, synth):
     """BASELINE config 5: 65 536 random DAGs, S=30 x E=5000: closure + score throughput, bit rows resident."""
     import torch
@@ -228,7 +263,7 @@ def run_gpu(args, rank, world, local_rank):
 
     _, _, D = synth.dataset(S, E, seed=0, alpha=ALPHA, beta=BETA)
     A, B = synth.nem_constants(ALPHA, BETA)
-    ds = nb.Dataset(D, A, B, device=dev)
+    ds = nb.Dataset(D, A, B, device=dev, sort_egenes=True)  # the score is a sum over E-genes: their stored order is free
     K, Wm = args.steps, max(args.warmup, 3)
     W = ds.W
 
@@ -290,6 +325,16 @@ def run_gpu(args, rank, world, local_rank):
         nb._lib.check(L.nemb200_score_batch(ds._h, C.c_void_p(closed.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
                                             C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
     ms_kernel = timed(score_only, K) / K
+    # the opt-in pair-merged table kernel (two attachment sites per look-up): planner + score, same batch
+    ms_pair = None
+    if ds.S >= 33 and ds.S <= 52 and ds.lut_valid:
+        def score_pair(k):
+            nb._lib.check(L.nemb200_score_batch(ds._h, C.c_void_p(closed.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
+                                                C.c_void_p(ws.data_ptr()), ws.numel(), nb.engine.SCORE_IMPLS["pair"], sp))
+        with torch.cuda.stream(stream):
+            for k in range(3):
+                score_pair(k)
+        ms_pair = timed(score_pair, K) / K
 
     # ---- e2e: public host API semantics - pinned host bit rows -> device, closure + score, scores -> host
     def e2e_step(k):
@@ -309,7 +354,7 @@ def run_gpu(args, rank, world, local_rank):
     lo, hi = parallel.shard_range(CHAINS * world, rank, world)
     state = nb.ChainState(ds, orders0[lo:hi], 2.0 * S / E, edge_counts=True, chain_offset=lo, seed=1234,
                           rule=nb.RULE_MASKED, cand=cand, use_nem=True)
-    state.run(max(Wm, 16))
+    state.run(max(Wm, 64))  # long enough to capture + instantiate the CUDA graph of the loop body (not part of a run)
     if world > 1:  # warm the collectives (NCCL communicator set-up is not part of a run)
         parallel.allreduce_edge_counts(state.edge_count_matrix())
         parallel.global_best(state.best_scores, state.best_orders, state.best_bits, lo)
@@ -361,7 +406,11 @@ def run_gpu(args, rank, world, local_rank):
                      "best_score": best[0], "edge_count_total": int(counts.sum().item())},
             "clocks": sampler.summary(),
         }
+        if ms_pair is not None:
+            out["score_pair_merged"] = {"ms_per_launch_incl_planner": ms_pair, "graph_scores_per_s": CHAINS / (ms_pair * 1e-3),
+                                        "note": "impl='pair' (opt-in): k_pair_plan + pair-merged k_score_tc + fallback + finalize"}
         if world == 1:
+            out["edge_fit"] = edge_fit_leg(nb, synth, not args.no_cpu)
             out["mcmc_small"] = small_mcmc_configs(nb, synth, not args.no_cpu)
             out["sweep_config5"] = config5_sweep(nb, synth)
         if world == 1 and not args.no_cpu:
