@@ -25,6 +25,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before the CUDA context exists (see nem_b200/__init__.py)
 
 S, E, CHAINS = 50, 10000, 1024
 ALPHA, BETA = 0.05, 0.1
@@ -336,16 +337,27 @@ def run_gpu(args, rank, world, local_rank):
                 score_pair(k)
         ms_pair = timed(score_pair, K) / K
 
-    # ---- e2e: public host API semantics - pinned host bit rows -> device, closure + score, scores -> host
-    def e2e_step(k):
-        closed_in = dev_bits[0]
-        closed_in.copy_(host_bits[(Wm + k) % n_batches], non_blocking=True)
-        sweep(closed_in)
-        host_scores.copy_(scores, non_blocking=True)
+    # ---- e2e: public host API semantics - pinned host bit rows -> device, closure + score, scores -> host, every
+    #      step; Dataset.score_stream double-buffers so the copy of step k+1 overlaps the kernels of step k
+    host_out = torch.empty((K, CHAINS), dtype=torch.float64).pin_memory()
+    ds.score_stream([host_bits[k % n_batches] for k in range(3)], host_out[:3])
+    torch.cuda.synchronize(dev)
+    e2e_batches = [host_bits[(Wm + k) % n_batches] for k in range(K)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(torch.cuda.current_stream(dev))
+    ds.score_stream(e2e_batches, host_out)
+    ev1.record(torch.cuda.current_stream(dev))
+    barrier()
+    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e2e.item())
+    # the e2e scores are the same numbers the device-resident sweep produces for the same batch
     with torch.cuda.stream(stream):
-        for k in range(3):
-            e2e_step(k)
-    ms_e2e = timed(e2e_step, K)
+        sweep(dev_bits[(Wm + K - 1) % n_batches])
+    torch.cuda.synchronize(dev)
+    assert torch.equal(host_out[K - 1], scores.cpu()), "e2e scores differ from the device-resident sweep"
 
     # ---- the full order-MCMC loop, device resident (propose -> closure -> score -> accept), MASKED rule so
     #      that every iteration runs the closure kernel (use_nem=True, nem_order_mcmc.py:283-284)
@@ -398,7 +410,7 @@ def run_gpu(args, rank, world, local_rank):
                          "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": flops,
                          "exps_per_launch": float((S + 1) * E * CHAINS), "peak_source": how},
             "e2e": {"value": CHAINS * world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch_bytes,
-                    "d2h_bytes_per_step": CHAINS * 8, "api": "closure + score_batch on pinned host bit rows, scores copied back"},
+                    "d2h_bytes_per_step": CHAINS * 8, "api": "Dataset.score_stream: closure + score_batch on pinned host bit rows, scores copied back, copies double-buffered against the kernels"},
             "gpu_launches": 3 * K,
             "mcmc": {"value": state.n * world * mc_iters / (ms_mcmc * 1e-3), "unit": "chain-iterations/s", "iters": mc_iters,
                      "chains": state.n * world, "ms_per_iter": ms_mcmc / mc_iters, "accept_rate": acc_rate,

@@ -199,6 +199,54 @@ class Dataset:
             _lib.check(_lib.lib().nemb200_closure_u32(_ptr(bits), bits.shape[0], self.S, _ptr(bits), _stream_ptr(st)))
         return self.score_bits(bits, impl).cpu().numpy()
 
+    def score_stream(self, host_batches, host_out, close: bool = True, impl="auto"):
+        """Score a sequence of equally-sized batches of bit-packed graphs that live in PINNED host memory
+        (`host_batches[k]`: int32 tensor (n,S,W)), writing float64 scores into the pinned `host_out[k]` (n,).
+        The host->device copy of batch k+1 runs on a copy stream while batch k is closed and scored, and the
+        scores go back asynchronously: two device buffers, no host synchronisation inside (the caller
+        synchronises once at the end).  This is the end-to-end form of closure + score_batch."""
+        if not len(host_batches):
+            return
+        dev = self.device
+        n = int(host_batches[0].shape[0])
+        if getattr(self, "_pipe", None) is None or self._pipe["n"] != n:
+            self._pipe = {"n": n, "copy": torch.cuda.Stream(dev), "comp": torch.cuda.Stream(dev), "back": torch.cuda.Stream(dev),
+                          "bits": [torch.empty((n, self.S, self.W), dtype=torch.int32, device=dev) for _ in range(2)],
+                          "scores": [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2)],
+                          "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
+                          "drained": [torch.cuda.Event() for _ in range(2)],
+                          "ws": torch.empty(max(_lib.lib().nemb200_score_workspace_bytes(self._h, n), 1), dtype=torch.uint8, device=dev)}
+        P = self._pipe
+        L = _lib.lib()
+        cur = torch.cuda.current_stream(dev)
+        P["copy"].wait_stream(cur)
+        P["comp"].wait_stream(cur)
+        P["back"].wait_stream(cur)
+        code = SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl)
+        for k, hb in enumerate(host_batches):
+            b = k & 1
+            with torch.cuda.stream(P["copy"]):
+                if k >= 2:
+                    P["copy"].wait_event(P["free"][b])      # batch k-2 no longer reads this buffer
+                P["bits"][b].copy_(hb, non_blocking=True)
+                P["ready"][b].record(P["copy"])
+            with torch.cuda.stream(P["comp"]):
+                P["comp"].wait_event(P["ready"][b])
+                if k >= 2:
+                    P["comp"].wait_event(P["drained"][b])   # the scores of batch k-2 have left this buffer
+                bits = P["bits"][b]
+                if close:
+                    _lib.check(L.nemb200_closure_u32(_ptr(bits), n, self.S, _ptr(bits), _stream_ptr(P["comp"])))
+                _lib.check(L.nemb200_score_batch(self._h, _ptr(bits), n, _ptr(P["scores"][b]), _ptr(P["ws"]), P["ws"].numel(),
+                                                 code, _stream_ptr(P["comp"])))
+                P["free"][b].record(P["comp"])
+            with torch.cuda.stream(P["back"]):               # scores go back on their own stream, off the kernels' path
+                P["back"].wait_event(P["free"][b])
+                host_out[k].copy_(P["scores"][b], non_blocking=True)
+                P["drained"][b].record(P["back"])
+        cur.wait_stream(P["comp"])
+        cur.wait_stream(P["back"])
+
     def order_graphs(self, orders, rule=RULE_FULL, cand=None, use_nem=True) -> torch.Tensor:
         """Bit rows of the graph each order induces (device tensor)."""
         o = torch.as_tensor(np.ascontiguousarray(np.asarray(orders, dtype=np.int32))).to(self.device)

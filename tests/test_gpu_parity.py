@@ -675,3 +675,21 @@ def test_mcmc_method_with_fitted_weights(nb):
     pos = np.empty(5, dtype=int); pos[mc.best_order] = np.arange(5)
     a, b = np.nonzero(best_dag)
     assert np.all(pos[a] < pos[b])           # only order-compatible edges (SURVEY Q7 fixed)
+
+
+def test_score_stream_pipelined_host_batches(nb):
+    """Dataset.score_stream (double-buffered host->device copies against closure + score) returns, batch for
+    batch, exactly what the synchronous API returns."""
+    S, E, n = 20, 900, 96
+    _, _, D = orc.synth_dataset(S, E, seed=3)
+    A, B = orc.nem_constants(0.05, 0.1)
+    ds = nb.Dataset(D, A, B)
+    rng = np.random.default_rng(0)
+    batches = [rand_dags(rng, n, S, p=0.2, closed=False) for _ in range(5)]
+    host = [torch.from_numpy(nb.pack_adj(b).view(np.int32)).pin_memory() for b in batches]
+    out = torch.zeros((5, n), dtype=torch.float64).pin_memory()
+    ds.score_stream(host, out)
+    torch.cuda.synchronize()
+    for k in range(5):
+        assert np.array_equal(out[k].numpy(), ds.score_graphs(batches[k], close=True)), k
+    ds.score_stream([], out)  # empty sequence is a no-op
