@@ -501,6 +501,78 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=S32 (2<<4), A=B=U8 (0), K-major, N>>3 at 17, M>>4 at 24
   const uint32_t idesc = (2u << 4) | ((uint32_t)(p.nmma >> 3) << 17) | ((128u >> 4) << 24);
 
+  // ---- B-operand expansion of one item by `nthr` cooperating threads (thread index te): bit rows -> u8 columns.
+  // The expander warps use it with 64 threads; the FIRST item of a CTA is expanded by all warps >= 2 (nothing
+  // else can run before the first operand exists, and 576 threads finish it four times sooner).
+  auto expand_std = [&](int g0, int ng, uint32_t bb, int te, int nthr, auto &&sync) {
+    const int gw = S * W;  // words per graph
+    for (int i = te; i < ng * gw; i += nthr) {
+      const int gi = i / gw;
+      const int gid = p.glist != nullptr ? p.glist[g0 + gi] : g0 + gi;
+      sRows[i] = p.phi[(size_t)gid * gw + (i - gi * gw)];
+    }
+    sync();
+    uint8_t *brow = smem + L::B + bb * 2 * kTileBytes;
+    float *bias = reinterpret_cast<float *>(smem + L::BIAS) + bb * 1024;
+    const int bstride = kBiasStride * (S > 64 ? 2 : 1);
+    const int CS = p.CS;
+    // padding sites (S <= j < CS) of the specialised kernels look up a table entry that is zero:
+    // offset 128*m with m odd is entry [q=(m-1)/2][p=32], zero as soon as 32 + (m-1)/2 > S
+    const uint32_t zero_m = S < 32 ? 1u : (uint32_t)(2 * (S - 32) + 3);
+    for (int col = te; col < (DBG(8) ? 0 : 256); col += nthr) {
+      const int gi = col / CS, j = col - gi * CS;
+      uint32_t anc[4] = {0u, 0u, 0u, 0u};
+      int cnt = 0;
+      const bool used = gi < ng && j < S;
+      if (used) {
+        const uint32_t *rows = sRows + gi * S * W;
+        const int jw = j >> 5, jb = j & 31;
+        for (int a = 0; a < S; ++a) {
+          uint32_t bit = ((rows[a * W + jw] >> jb) & 1u) | (a == j ? 1u : 0u);
+          anc[a >> 5] |= bit << (a & 31);
+          cnt += (int)bit;
+        }
+      }
+      // table look-up sites get the extra K row S: B = lut_base/128 (A holds 128 there), so that the
+      // accumulator is the shared-memory address of lut[q][p]; unused columns point at lut[0][0]
+      bool lut_site = EPI == EPI_LUT && gi < G;
+      if constexpr (S_T > 0) lut_site = lut_site && is_lut_site<S_T, NLUT>(j);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t half = (anc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+        uint4 v;
+        v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+        v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+        v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+        v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+        if (lut_site && c == (S >> 4)) {
+          uint32_t extv = ((sbase + L::LUT) >> 7) + (j >= S ? zero_m : 0u);
+          if (extv > 255u) asm volatile("trap;");  // the table must sit in the first 32 KB of shared memory
+          uint32_t ext = extv << ((S & 3) * 8);
+          int wsel = (S >> 2) & 3;
+          if (wsel == 0) v.x |= ext; else if (wsel == 1) v.y |= ext; else if (wsel == 2) v.z |= ext; else v.w |= ext;
+        }
+        *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
+      }
+      if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  };
+  constexpr int kWideThreads = cta_threads(S_T) - 64;  // warps >= 2
+  if constexpr (!PAIR) {
+    if (warp >= 2) {
+      Walker wk0(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
+      Item i0;
+      if (wk0.next(i0, p.n_mtiles)) {  // CTA-uniform
+        const int g0 = i0.ntile * G;
+        expand_std(g0, min(G, n_graphs - g0), 0u, (int)threadIdx.x - 64, kWideThreads,
+                   [] { asm volatile("bar.sync 7, %0;" ::"n"(kWideThreads) : "memory"); });
+        asm volatile("bar.sync 7, %0;" ::"n"(kWideThreads) : "memory");  // every column is written and fenced
+        if (warp < 4 && lane == 0) mbar_arrive(bar_bfull);               // the two arrivals the barrier expects
+      }
+    }
+  }
+
   if (warp == 0) {
     // =============================== TMA producer: A tiles of every item, in order ===================
     if (lane == 0) {
@@ -558,13 +630,9 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       const int g0 = ntile * G, ng = min(G, n_graphs - g0);
       const uint32_t bb = k & 1u;
       if (k >= 2) mbar_wait(bar_edone + 8 * bb, ((k - 2) >> 1) & 1u);  // epilogue finished the item that used this buffer
-      const int gw = S * W;  // words per graph
-      for (int i = te; i < (PAIR ? 0 : ng * gw); i += 64) {
-        const int gi = i / gw;
-        const int gid = p.glist != nullptr ? p.glist[g0 + gi] : g0 + gi;
-        sRows[i] = p.phi[(size_t)gid * gw + (i - gi * gw)];
-      }
-      asm volatile("bar.sync 6, 64;" ::: "memory");
+      if (!PAIR && k == 0) continue;  // expanded by all warps above
+      if constexpr (!PAIR) expand_std(g0, ng, bb, te, 64, [] { asm volatile("bar.sync 6, 64;" ::: "memory"); });
+      else asm volatile("bar.sync 6, 64;" ::: "memory");
       uint8_t *brow = smem + L::B + bb * 2 * kTileBytes;
       if constexpr (PAIR) {
         // ---- pair-merged columns: the planner (k_pair_plan) wrote every column's 64 operand bytes and the shape
@@ -601,50 +669,6 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
           brow[sw128((uint32_t)col, (uint32_t)(S + 8))] = (uint8_t)((addr & 127u) >> 2);
           if (c == 0) sTot[gi] = meta.z;  // table entries of graph gi (0 for absent / unplanned graphs)
         }
-      } else {
-      float *bias = reinterpret_cast<float *>(smem + L::BIAS) + bb * 1024;
-      const int bstride = kBiasStride * (S > 64 ? 2 : 1);
-      const int CS = p.CS;
-      // padding sites (S <= j < CS) of the specialised kernels look up a table entry that is zero:
-      // offset 128*m with m odd is entry [q=(m-1)/2][p=32], zero as soon as 32 + (m-1)/2 > S
-      const uint32_t zero_m = S < 32 ? 1u : (uint32_t)(2 * (S - 32) + 3);
-      for (int col = te; col < (DBG(8) ? 0 : 256); col += 64) {
-        const int gi = col / CS, j = col - gi * CS;
-        uint32_t anc[4] = {0u, 0u, 0u, 0u};
-        int cnt = 0;
-        const bool used = gi < ng && j < S;
-        if (used) {
-          const uint32_t *rows = sRows + gi * S * W;
-          const int jw = j >> 5, jb = j & 31;
-          for (int a = 0; a < S; ++a) {
-            uint32_t bit = ((rows[a * W + jw] >> jb) & 1u) | (a == j ? 1u : 0u);
-            anc[a >> 5] |= bit << (a & 31);
-            cnt += (int)bit;
-          }
-        }
-        // table look-up sites get the extra K row S: B = lut_base/128 (A holds 128 there), so that the
-        // accumulator is the shared-memory address of lut[q][p]; unused columns point at lut[0][0]
-        bool lut_site = EPI == EPI_LUT && gi < G;
-        if constexpr (S_T > 0) lut_site = lut_site && is_lut_site<S_T, NLUT>(j);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t half = (anc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-          uint4 v;
-          v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-          v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-          v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-          v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-          if (lut_site && c == (S >> 4)) {
-            uint32_t extv = ((sbase + L::LUT) >> 7) + (j >= S ? zero_m : 0u);
-            if (extv > 255u) asm volatile("trap;");  // the table must sit in the first 32 KB of shared memory
-            uint32_t ext = extv << ((S & 3) * 8);
-            int wsel = (S >> 2) & 3;
-            if (wsel == 0) v.x |= ext; else if (wsel == 1) v.y |= ext; else if (wsel == 2) v.z |= ext; else v.w |= ext;
-          }
-          *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
-        }
-        if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
-      }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
