@@ -30,6 +30,9 @@ struct nemb200_dataset {
   float *tabs;        // compact exp table of the pair planner: tabs[n(n+1)/2 + p] = lut[n-p][p], n <= S
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)
   double *sumN;       // [1] A * sum(D)   (nem.py:62 summed over e)
+  int *counters;      // [64] self-resetting completion counters of the score kernel's fused finalize (zero at rest)
+  const void *ctr_ws[64];  // host: which score workspace owns which counter
+  int n_ctr;
   // one cached CUDA graph of the MCMC iteration body (re-used while the same buffers are passed)
   unsigned long long mcmc_graph_key;
   void *mcmc_graph_exec;  // cudaGraphExec_t

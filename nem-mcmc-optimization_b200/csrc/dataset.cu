@@ -22,7 +22,7 @@ namespace {
 // pair-merged table kernel (score_tc.cu): 32 accumulator columns per graph, S + 9 K rows <= 64
 bool pair_supported(int S) { return S >= 33 && S <= 52; }
 
-struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, sumN, total; int W, n_mtiles; };
+struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, sumN, counters, total; int W, n_mtiles; };
 Layout make_layout(int S, int E) {
   Layout L;
   L.W = (S + 31) / 32;
@@ -34,6 +34,7 @@ Layout make_layout(int S, int E) {
   L.lut = off; off = align_up(off + 64 * 64 * 4, 1024);
   L.tabs = off; off = align_up(off + 65 * 66 / 2 * 4, 1024);
   L.sumN = off; off = align_up(off + 8, 1024);
+  L.counters = off; off = align_up(off + 64 * 4, 1024);
   L.total = off;
   return L;
 }
@@ -124,6 +125,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   h->alpha2 = -A * NEMB200_LOG2E; h->beta2 = B * NEMB200_LOG2E;
   h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_pair = base + L.a_pair;
   h->lut = (float *)(base + L.lut); h->tabs = (float *)(base + L.tabs); h->sumN = (double *)(base + L.sumN);
+  h->counters = (int *)(base + L.counters);
   // single-scale validity: largest log2-domain value over the lattice p+q<=S
   double vmax = 0.0;
   if (h->alpha2 > 0) vmax = fmax(vmax, h->alpha2 * S);
@@ -140,6 +142,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   h->G = h->G >= 4 ? (h->G & ~3) : 2;           // epilogue warpgroup), or 2 for S > 64
   h->G_lut = h->G;  // the specialised table kernel may use its own tile width (score_tc.cu: tile_graphs)
   int E_pad = L.n_mtiles * 128;
+  if (cudaMemsetAsync(h->counters, 0, 64 * sizeof(int), st) != cudaSuccess) { free(h); nemb200_set_error("cudaMemsetAsync failed"); return -2; }
   k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
   k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 0, h->a_lut);
   h->pair_ok = h->lut_valid && pair_supported(S);

@@ -88,6 +88,10 @@ struct Params {
   // list mode (fallback pass of the pair kernel): graph ids and their count live in device memory
   const int *glist;
   const int *n_dev;
+  // fused finalize: the last CTA to finish sums the partials of every graph (self-resetting counter); NULL = separate k_finalize
+  int *done_counter;
+  const double *sumN;
+  double *scores;
   long long *trace;      // diagnostics only: clock64 time line of CTA 0 (NULL normally)
   int debug;             // diagnostics only (NEMB200_DEBUG): 1 skip epilogue math, 2 skip MMA, 4 skip TMA, 8 skip expansion
 };
@@ -222,9 +226,10 @@ __host__ __device__ inline int effective_ctas(unsigned T, int n_mtiles, int max_
   return (int)(c < (unsigned)max_ctas ? c : (unsigned)max_ctas);
 }
 // first flat tile of CTA c: ranges [c*T/ctas, (c+1)*T/ctas); T * ctas < 2^32 is checked by the host
-__host__ __device__ inline unsigned cta_first_tile(unsigned c, unsigned T, unsigned ctas) { return (unsigned)(((unsigned long long)c * T) / ctas); }
+// (32-bit arithmetic: the host guarantees T * ctas + T < 2^32; 64-bit divisions are emulated and slow on the device)
+__host__ __device__ inline unsigned cta_first_tile(unsigned c, unsigned T, unsigned ctas) { return (c * T) / ctas; }
 __host__ __device__ inline int cta_of_tile(unsigned x, unsigned T, unsigned ctas) {  // owner of flat tile x
-  return (int)(((unsigned long long)(x + 1) * ctas + T - 1) / T) - 1;
+  return (int)(((x + 1u) * ctas + T - 1u) / T) - 1;
 }
 __host__ __device__ inline int slots_of_ntile(int ntile, int n_mtiles, unsigned T, int ctas) {
   const unsigned lo = (unsigned)ntile * (unsigned)n_mtiles;
@@ -750,6 +755,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
         double v = 0.0;
         for (int w4 = 0; w4 < 4; ++w4) v += sRed[(wg * 4 + w4) * 8 + tw];
         p.partials[(size_t)(g0 + tw) * p.n_slots + item_slot(ntile, n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x)] = v;  // list mode: indexed by list position
+        if (p.done_counter != nullptr) __threadfence();  // visible to the CTA that finalizes (below)
       }
       wg_bar_sync(wg);
     }
@@ -757,6 +763,28 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  if (p.done_counter != nullptr) {
+    // ---- fused finalize ("last block" pattern): score = sum_e N[e] + ln2 * sum of the graph's partial sums
+    volatile int *s_last = reinterpret_cast<volatile int *>(sRows);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *s_last = atomicAdd(p.done_counter, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      const unsigned T = (unsigned)n_ntiles * (unsigned)p.n_mtiles;
+      const double sumN = *p.sumN;
+      for (int g = threadIdx.x; g < n_graphs; g += cta_threads(S_T)) {
+        const int cnt = slots_of_ntile(g / G, p.n_mtiles, T, (int)gridDim.x);
+        const double *src = p.partials + (size_t)g * p.n_slots;
+        double v = 0.0;
+        for (int c = 0; c < cnt && c < p.n_slots; ++c) v += __ldcg(src + c);
+        p.scores[g] = sumN + NEMB200_LN2 * v;
+      }
+      if (threadIdx.x == 0) *p.done_counter = 0;  // ready for the next launch on this workspace
+    }
+  }
 }
 
 // ---- pair planner --------------------------------------------------------------------------------------
@@ -1075,6 +1103,18 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   p.kc = (float)(256.0 * kappa2 / 252.0 + h->beta2);
   p.scale = impl == NEMB200_SCORE_TC_EX2_2PASS ? 0.f : (float)h->scale;
   p.plan = nullptr; p.tables = nullptr; p.glist = nullptr; p.n_dev = nullptr;
+  p.done_counter = nullptr; p.sumN = h->sumN; p.scores = scores;
+  // (one CTA finalizing a large batch is slower than the separate, fully parallel kernel; in the two-group MCMC loop
+  //  the separate kernel overlaps with the other group's score kernel and the tail of a fused one does not)
+  if (!pair && n <= 2048 && leave_sms_free == 0) {
+    // one self-resetting completion counter per distinct workspace (launches that share a workspace are ordered by
+    // the caller anyway); when the pool is exhausted the separate finalize kernel is used
+    nemb200_dataset *hm = const_cast<nemb200_dataset *>(h);
+    int slot = -1;
+    for (int i = 0; i < hm->n_ctr; ++i) if (hm->ctr_ws[i] == ws) { slot = i; break; }
+    if (slot < 0 && hm->n_ctr < 64) { slot = hm->n_ctr++; hm->ctr_ws[slot] = ws; }
+    if (slot >= 0) p.done_counter = h->counters + slot;
+  }
   const int grid = effective_ctas(T, h->n_mtiles, nsm);
   int rc;
   static const char *dbg_env = getenv("NEMB200_DEBUG");
@@ -1112,6 +1152,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
     return -1;
   }
   if (rc) return rc;
+  if (p.done_counter != nullptr) return 0;  // finalized by the last CTA of the score kernel
   // 64-thread CTAs: small enough (registers) to run beside a resident score CTA of another stream (two-group MCMC loop)
   k_finalize<<<(n + 63) / 64, 64, 0, st>>>(p.partials, p.n_slots, G, h->n_mtiles, nsm, h->sumN, n, scores, fbslot,
                                                reinterpret_cast<const int *>(wb + wl.fcount),
