@@ -7,14 +7,7 @@ Drop-in mirrors of the reference's flat modules (MrGreyPanda/NEM-MCMC-optimizati
 plus the batched device entry points in nem_b200.engine (Dataset.score_graphs, closure, run_chains).
 All compute runs in hand-written CUDA behind the C ABI of include/nemb200.h; there is no CPU fallback.
 """
-import os as _os
-
-# The two-group MCMC loop and Dataset.score_stream rely on independent streams really running concurrently.  With
-# the default of 8 hardware work queues, streams alias once a process has created a handful of them and parallel
-# CUDA-graph branches serialise (measured: 108 -> 190 us/iteration).  Must be set before the CUDA context exists.
-_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
-from . import _lib, engine, utils, nem, nem_order_mcmc, parallel, synth  # noqa: F401,E402
+from . import _lib, engine, utils, nem, nem_order_mcmc, parallel, synth  # noqa: F401
 from .engine import Dataset, ChainState, ChainResult, closure, pack_adj, unpack_adj, RULE_FULL, RULE_MASKED  # noqa: F401
 from .nem import NEM  # noqa: F401
 from .nem_order_mcmc import NEMOrderMCMC, replica_exchange_method  # noqa: F401

@@ -229,14 +229,14 @@ class Dataset:
                 if k >= 2:
                     P["copy"].wait_event(P["free"][b])      # batch k-2 no longer reads this buffer
                 P["bits"][b].copy_(hb, non_blocking=True)
+                if close:  # the closure of batch k+1 also runs beside the score kernel of batch k
+                    _lib.check(L.nemb200_closure_u32(_ptr(P["bits"][b]), n, self.S, _ptr(P["bits"][b]), _stream_ptr(P["copy"])))
                 P["ready"][b].record(P["copy"])
             with torch.cuda.stream(P["comp"]):
                 P["comp"].wait_event(P["ready"][b])
                 if k >= 2:
                     P["comp"].wait_event(P["drained"][b])   # the scores of batch k-2 have left this buffer
                 bits = P["bits"][b]
-                if close:
-                    _lib.check(L.nemb200_closure_u32(_ptr(bits), n, self.S, _ptr(bits), _stream_ptr(P["comp"])))
                 _lib.check(L.nemb200_score_batch(self._h, _ptr(bits), n, _ptr(P["scores"][b]), _ptr(P["ws"]), P["ws"].numel(),
                                                  code, _stream_ptr(P["comp"])))
                 P["free"][b].record(P["comp"])
