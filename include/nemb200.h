@@ -167,6 +167,11 @@ int nemb200_synth_knockdown(const uint32_t *d_adj_bits, const int32_t *d_end_nod
 int nemb200_edge_counts_reduce(const uint32_t *d_edge_counts, int n_chains, int S,
                                int64_t *d_out, void *stream);
 
+/* ---- host-only self-test of the score kernel's work partition (no device work; used by the CPU tests):
+ *      0 if every (N tile, E tile) pair is owned by exactly one CTA and every N tile has a dense set of at most
+ *      24 partial-sum slots for this problem size. */
+int nemb200_selftest_partition(int n_ntiles, int n_mtiles, int max_ctas);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,18 +14,18 @@
 // lut[q][p] = 2^(alpha2*p + beta2*q - s).  Epilogue "LUT": one LDS + one FADD per (site, E-gene); an extra
 // K row adds the table's shared-memory base so the accumulator IS the address.  Epilogue "EX2": the same
 // accumulator is mapped linearly to the log2-domain value and exponentiated with ex2.approx (any S<=128);
-// "EX2_2PASS" subtracts the running maximum first (any dynamic range).  For the headline shapes the
-// epilogue is compiled for a fixed S and splits each graph's sites between the two pipes (LSU table
-// look-ups and MUFU ex2) so that neither is the single limiter.
-// No B x S x E intermediate ever reaches HBM: per (graph, E-chunk, warpgroup) one double is written.
+// "EX2_2PASS" subtracts the running maximum first (any dynamic range).  For every S <= 63 the table epilogue is
+// compiled for a fixed column stride (straight-line, software-pipelined over tiles).  "PAIR" (opt-in): a planner
+// merges pairs of sites so that one look-up serves two of them (k_pair_plan below).
+// No B x S x E intermediate ever reaches HBM: per (graph, CTA piece of its N tile) one double is written.
 //
 // Roles (640 threads, no CTA-wide barrier in the main loop): warp 0 = TMA producer (A tiles, 4-stage
 // mbarrier ring), warp 1 = MMA issuer + TMEM owner (2 x 256-column accumulators), warps 2-3 = B-operand
-// expanders (double-buffered, run one work item ahead), warps 4-19 = four epilogue warpgroups.  All four
-// drain the SAME accumulator buffer (each takes a quarter of the tile's graphs) while the MMA of the next
-// tile fills the other buffer, so the MMA + mbarrier hand-shake latency is hidden behind epilogue work and
-// four warps per scheduler hide the LDS / MUFU / TMEM latencies.  Work items (N tile of G graphs x chunk
-// of E tiles) are statically strided over CTAs.
+// expanders (double-buffered, run one work item ahead; the first item is expanded by all warps >= 2),
+// warps 4-19 = four epilogue warpgroups.  All four drain the SAME accumulator buffer (each takes a quarter of
+// the tile's graphs) while the MMA of the next tile fills the other buffer.  The flattened (N tile, E tile) grid
+// is cut into one contiguous range per CTA (Walker); for small batches the last CTA to finish reduces the
+// partial sums (fused finalize).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -1158,5 +1158,36 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
                                                reinterpret_cast<const int *>(wb + wl.fcount),
                                                reinterpret_cast<const double *>(wb + wl.fb_partials), h->G_lut);
   NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Host-only self-test of the tile partition (no device work): every flat tile is owned by exactly one CTA, the items a
+// CTA walks are contiguous and inside one N tile, slots are dense per N tile and never exceed kMaxSlots.  Returns 0 if
+// all invariants hold, else a positive code.  Used by the CPU test-suite.
+extern "C" int nemb200_selftest_partition(int n_ntiles, int n_mtiles, int max_ctas) {
+  if (n_ntiles < 1 || n_mtiles < 1 || max_ctas < 1) return -1;
+  if ((double)n_ntiles * n_mtiles * (max_ctas + 1.0) >= 4.0e9) return -1;
+  const unsigned T = (unsigned)n_ntiles * (unsigned)n_mtiles;
+  const int ctas = effective_ctas(T, n_mtiles, max_ctas);
+  if (ctas < 1 || ctas > max_ctas) return 1;
+  unsigned expect = 0;
+  for (int c = 0; c < ctas; ++c) {
+    const unsigned lo = cta_first_tile(c, T, ctas), hi = cta_first_tile(c + 1, T, ctas);
+    if (lo != expect || hi < lo) return 2;
+    expect = hi;
+    for (unsigned x = lo; x < hi; ++x)
+      if (cta_of_tile(x, T, ctas) != c) return 3;
+  }
+  if (expect != T) return 4;
+  for (int nt = 0; nt < n_ntiles; ++nt) {
+    const int cnt = slots_of_ntile(nt, n_mtiles, T, ctas);
+    if (cnt < 1 || cnt > kMaxSlots) return 5;
+    const unsigned lo = (unsigned)nt * n_mtiles;
+    const int first = cta_of_tile(lo, T, ctas);
+    for (int m = 0; m < n_mtiles; ++m) {
+      const int slot = cta_of_tile(lo + m, T, ctas) - first;
+      if (slot < 0 || slot >= cnt) return 6;
+    }
+  }
   return 0;
 }

@@ -137,3 +137,17 @@ def test_bench_reference_arm_runs_on_cpu():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == "nem_graph_scores_per_s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_score_kernel_partition_invariants():
+    """The flat (N tile, E tile) partition of the score kernel (csrc/score_tc.cu: Walker / k_finalize): host-only
+    self-test over many problem sizes - every tile owned once, dense slots, at most 24 per N tile."""
+    import nem_b200
+    L = nem_b200._lib.lib()
+    rng = np.random.default_rng(0)
+    cases = [(1, 1, 148), (1, 79, 148), (256, 79, 148), (128, 79, 128), (205, 79, 148), (1024, 40, 148), (8192, 40, 148),
+             (2, 782, 148), (16384, 782, 132), (3, 5, 7), (1000, 1, 148), (1, 1000, 148)]
+    cases += [(int(rng.integers(1, 3000)), int(rng.integers(1, 900)), int(rng.integers(1, 160))) for _ in range(60)]
+    for nt, nm, c in cases:
+        assert L.nemb200_selftest_partition(nt, nm, c) == 0, (nt, nm, c)
+    assert L.nemb200_selftest_partition(0, 1, 1) < 0
