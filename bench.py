@@ -283,7 +283,7 @@ def run_gpu(args, rank, world, local_rank):
     import ctypes as C
     stream = torch.cuda.Stream(dev)
     sp = C.c_void_p(stream.cuda_stream)
-    ws, _ = ds._score_workspace(CHAINS)
+    ws, _ = ds._score_workspace(CHAINS, "pair" if 33 <= S <= 52 else "auto")  # big enough for the opt-in pair leg too
 
     def sweep(bits):
         nb._lib.check(L.nemb200_closure_u32(C.c_void_p(bits.data_ptr()), CHAINS, S, C.c_void_p(closed.data_ptr()), sp))

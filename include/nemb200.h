@@ -73,6 +73,9 @@ int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_
  *      sum_e N[e] + sum_e LSE(0, ((I|Phi)^T T)[:,e]).  d_scores: n_graphs float64.
  *      d_workspace: nemb200_score_workspace_bytes(h, n_graphs) bytes. */
 size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs);
+/* the same for one specific `impl`: NEMB200_SCORE_TC_PAIR needs room for its plan and pair tables
+ * (about 9 KB per graph); every other implementation fits nemb200_score_workspace_bytes(). */
+size_t nemb200_score_workspace_bytes_impl(const nemb200_dataset *h, int n_graphs, int impl);
 int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_phi_bits, int n_graphs,
                         double *d_scores, void *d_workspace, size_t workspace_bytes, int impl,
                         void *stream);

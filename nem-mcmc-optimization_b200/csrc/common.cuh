@@ -67,7 +67,7 @@ int launch_order_to_graph(const int32_t *orders, int n, int S, int rule, const u
 size_t score_witness_workspace_bytes(int n);
 int launch_score_witness(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws,
                          cudaStream_t st);
-size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n);
+size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair = false);
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
                     int impl, cudaStream_t st, int leave_sms_free = 0);
 

@@ -30,7 +30,7 @@ size_t carve(const nemb200_dataset *h, int n, void *base, McmcWs *w) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   size_t o_iter = take(16), o_since = take(8 * (size_t)n), o_po = take(4 * (size_t)n * h->S),
          o_pb = take(4 * (size_t)n * h->S * h->W), o_ps = take(8 * (size_t)n);
-  size_t sws = score_tc_workspace_bytes(h, n), wws = score_witness_workspace_bytes(n);
+  size_t sws = score_tc_workspace_bytes(h, n, /*with_pair=*/true), wws = score_witness_workspace_bytes(n);  // chains are few: room for impl = PAIR
   if (wws > sws) sws = wws;
   size_t o_sw = take(sws);
   if (w) {
@@ -270,10 +270,13 @@ static int score_dispatch(const nemb200_dataset *h, const uint32_t *phi, int n, 
   return launch_score_tc(h, phi, n, scores, ws, ws_bytes, impl, st, leave_sms_free);
 }
 
-extern "C" size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs) {
+extern "C" size_t nemb200_score_workspace_bytes_impl(const nemb200_dataset *h, int n_graphs, int impl) {
   if (!h || n_graphs < 0) return 0;
-  size_t a = score_tc_workspace_bytes(h, n_graphs), b = score_witness_workspace_bytes(n_graphs);
+  size_t a = score_tc_workspace_bytes(h, n_graphs, impl == NEMB200_SCORE_TC_PAIR), b = score_witness_workspace_bytes(n_graphs);
   return a > b ? a : b;
+}
+extern "C" size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs) {
+  return nemb200_score_workspace_bytes_impl(h, n_graphs, NEMB200_SCORE_AUTO);
 }
 
 extern "C" int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_phi_bits, int n_graphs, double *d_scores,

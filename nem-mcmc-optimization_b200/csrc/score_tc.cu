@@ -1045,16 +1045,17 @@ int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t
 
 // workspace carve-up (bytes from the base)
 struct WsLay { size_t fcount, partials, fb_partials, plan, tables, fbslot, flist, trace, total; };
-WsLay ws_layout(const nemb200_dataset *h, int n) {
+WsLay ws_layout(const nemb200_dataset *h, int n, bool with_pair) {
   WsLay w;
+  const bool pr = with_pair && h->pair_ok;
   size_t off = 0;
   w.fcount = off; off += 256;
   w.partials = off; off = align_up(off + sizeof(double) * (size_t)(n + 16) * kMaxSlots, 256);
-  w.fb_partials = off; off = align_up(off + (h->pair_ok ? sizeof(double) * (size_t)(n + 16) * kMaxSlots : 0), 256);
-  w.plan = off; off = align_up(off + (h->pair_ok ? (size_t)n * kPairCS * kPlanColBytes : 0), 256);
-  w.tables = off; off = align_up(off + (h->pair_ok ? (size_t)n * kPairCap * 4 : 0), 256);
-  w.fbslot = off; off = align_up(off + (h->pair_ok ? (size_t)n * 4 : 0), 256);
-  w.flist = off; off = align_up(off + (h->pair_ok ? (size_t)(n + 16) * 4 : 0), 256);
+  w.fb_partials = off; off = align_up(off + (pr ? sizeof(double) * (size_t)(n + 16) * kMaxSlots : 0), 256);
+  w.plan = off; off = align_up(off + (pr ? (size_t)n * kPairCS * kPlanColBytes : 0), 256);
+  w.tables = off; off = align_up(off + (pr ? (size_t)n * kPairCap * 4 : 0), 256);
+  w.fbslot = off; off = align_up(off + (pr ? (size_t)n * 4 : 0), 256);
+  w.flist = off; off = align_up(off + (pr ? (size_t)(n + 16) * 4 : 0), 256);
   w.trace = off; off += 8 * 8192;  // diagnostics time line
   w.total = off;
   return w;
@@ -1062,7 +1063,7 @@ WsLay ws_layout(const nemb200_dataset *h, int n) {
 
 }  // namespace
 
-size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n) { return ws_layout(h, n).total; }
+size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair) { return ws_layout(h, n, with_pair).total; }
 
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
                     int impl, cudaStream_t st, int leave_sms_free) {
@@ -1074,7 +1075,9 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_PAIR || h->pair_ok, "pair-merged table epilogue not available for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUT || h->lut_valid, "exp-table epilogue not valid for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_EX2 || h->fixed_valid, "fixed-scale ex2 epilogue not valid for this dataset");
-  NEMB_REQUIRE(ws_bytes >= score_tc_workspace_bytes(h, n), "score workspace too small");
+  NEMB_REQUIRE(ws_bytes >= score_tc_workspace_bytes(h, n, impl == NEMB200_SCORE_TC_PAIR),
+               impl == NEMB200_SCORE_TC_PAIR ? "score workspace too small for the pair-merged kernel: size it with nemb200_score_workspace_bytes_impl"
+                                             : "score workspace too small");
   if (n == 0) return 0;
   // leave_sms_free: the two-group MCMC loop keeps a few SMs out of each score launch so that the other group's
   // propose / accept / finalize kernels (and the first CTAs of its score kernel) never queue behind a full wave
@@ -1083,7 +1086,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   const bool lut = impl == NEMB200_SCORE_TC_LUT;
   const int G = pair ? kPairG : (lut ? h->G_lut : h->G);  // graphs per MMA N tile of the kernel that will run
   const int CS = pair ? kPairCS : h->CS;
-  const WsLay wl = ws_layout(h, n);
+  const WsLay wl = ws_layout(h, n, pair);
   uint8_t *wb = reinterpret_cast<uint8_t *>(ws);
   const int n_ntiles = (n + G - 1) / G;
   NEMB_REQUIRE((double)n_ntiles * h->n_mtiles * nsm < 4.0e9 && (double)((n + 1) / 2 + 1) * h->n_mtiles * nsm < 4.0e9,

@@ -170,8 +170,9 @@ class Dataset:
             pass
 
     # ---- batched score -------------------------------------------------------------------------
-    def _score_workspace(self, n):
-        need = _lib.lib().nemb200_score_workspace_bytes(self._h, n)
+    def _score_workspace(self, n, impl="auto"):
+        code = SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl)
+        need = _lib.lib().nemb200_score_workspace_bytes_impl(self._h, n, code)
         if self._score_ws is None or self._score_ws.numel() < need:
             self._score_ws = torch.empty(max(need, 1), dtype=torch.uint8, device=self.device)
         return self._score_ws, need
@@ -181,7 +182,7 @@ class Dataset:
         n = int(bits.shape[0])
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=self.device)
-        ws, need = self._score_workspace(n)
+        ws, need = self._score_workspace(n, impl)
         st = stream or torch.cuda.current_stream(self.device)
         _lib.check(_lib.lib().nemb200_score_batch(self._h, _ptr(bits), n, _ptr(out), _ptr(ws), ws.numel(),
                                                   SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl),
@@ -215,7 +216,8 @@ class Dataset:
                           "scores": [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2)],
                           "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
                           "drained": [torch.cuda.Event() for _ in range(2)],
-                          "ws": torch.empty(max(_lib.lib().nemb200_score_workspace_bytes(self._h, n), 1), dtype=torch.uint8, device=dev)}
+                          "ws": torch.empty(max(_lib.lib().nemb200_score_workspace_bytes_impl(self._h, n, SCORE_IMPLS["pair"]), 1),
+                                            dtype=torch.uint8, device=dev)}
         P = self._pipe
         L = _lib.lib()
         cur = torch.cuda.current_stream(dev)

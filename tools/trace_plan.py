@@ -11,7 +11,7 @@ bits = ds.order_graphs(nb.synth.random_orders(n, S, 1), rule=1, cand=(np.random.
 for _ in range(3): ds.score_bits(bits, impl="pair")
 torch.cuda.synchronize()
 ws = ds._score_ws
-need = nb._lib.lib().nemb200_score_workspace_bytes(ds._h, n)
+need = ds._score_ws.numel()  # the diagnostics time line sits at the end of the workspace that was used
 tr = ws[need - 8 * 8192: need - 8 * 8192 + 9 * 8].cpu().numpy().view(np.int64)
 names = ["load", "anc", "count", "rank", "costs", "greedy", "select", "emit", "tables"]
 print(" ".join(f"{names[i]}={tr[i + 1] - tr[i]}" for i in range(8)), "total", tr[8] - tr[0])

@@ -11,7 +11,7 @@ bits = ds.order_graphs(nb.synth.random_orders(n, S, 1), rule=1, cand=(np.random.
 for _ in range(3): ds.score_bits(bits)
 torch.cuda.synchronize()
 ws = ds._score_ws
-need = nb._lib.lib().nemb200_score_workspace_bytes(ds._h, n)
+need = ds._score_ws.numel()  # the diagnostics time line sits at the end of the workspace that was used
 tr_off = need - 8 * 8192
 ws[tr_off:tr_off + 8 * 8192].zero_()
 ds.score_bits(bits); torch.cuda.synchronize()
