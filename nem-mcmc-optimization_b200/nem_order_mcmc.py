@@ -207,7 +207,7 @@ class NEMOrderMCMC:
         all chains is returned and `edge_freq` holds the posterior edge frequencies."""
         if rule == "fit":
             return self._method_fit(swap_prob, gamma, seed, n_iterations, verbose, use_nem)
-        ds = self.nem.dataset
+        ds = getattr(self.nem, "score_dataset", self.nem.dataset)
         orders0 = start_orders(self.perm_order, n_chains, seed)
         gam = np.broadcast_to(np.asarray(gamma, dtype=np.float64), (n_chains,))
         state = engine.ChainState(ds, orders0, gam, edge_counts=True, seed=seed, rule=_RULES[rule], cand=cand,
@@ -300,7 +300,7 @@ def replica_exchange_method(nem, n_exchange, n_iter, init_order_guess, n_replica
     gammas = np.tile((1.0 + 0.2 * np.arange(n_replicas)) * S / E, n_ladders)
     orders0 = start_orders(init_order_guess, n, seed)
     orders0[::n_replicas] = np.asarray(init_order_guess, dtype=np.int32)
-    state = engine.ChainState(nem.dataset, orders0, gammas, edge_counts=False, seed=seed, rule=_RULES[rule], cand=cand,
+    state = engine.ChainState(getattr(nem, "score_dataset", nem.dataset), orders0, gammas, edge_counts=False, seed=seed, rule=_RULES[rule], cand=cand,
                               use_nem=use_nem)
     n_swaps = 0
     for r in range(n_exchange):
