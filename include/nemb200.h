@@ -38,7 +38,8 @@ enum {
   NEMB200_SCORE_TC_EX2 = 3,  /* tcgen05 GEMM + ex2 epilogue, fixed scale */
   NEMB200_SCORE_TC_EX2_2PASS = 4, /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
   NEMB200_MCMC_FUSED = 5, /* nemb200_mcmc_run only: persistent one-CTA-per-chain kernel (small S*E) */
-  NEMB200_SCORE_TC_PAIR = 6 /* tcgen05 GEMM + pair-merged table epilogue: two attachment sites per look-up (33 <= S <= 52) */
+  NEMB200_SCORE_TC_PAIR = 6, /* tcgen05 GEMM + pair-merged table epilogue: two attachment sites per look-up (33 <= S <= 52) */
+  NEMB200_SCORE_TC_LUTM = 7  /* tcgen05 GEMM + multi-level exp-table epilogue: any dynamic range, 64 <= S <= 118 */
 };
 
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */
@@ -57,7 +58,8 @@ int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A, double B,
                            nemb200_dataset **out);
 int nemb200_dataset_destroy(nemb200_dataset *h);
 /* host-side facts about the dataset: fills info[0..7] =
- * {S, E, W, K_pad, graphs_per_tile, lut_valid, scale_log2, n_mtiles} */
+ * {S, E, W, K_pad, graphs_per_tile, lut_valid, scale_log2, n_mtiles}; with n >= 9 also info[8] = number of levels
+ * of the multi-level exp table (NEMB200_SCORE_TC_LUTM; 0 = not usable for this dataset) */
 int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int n);
 
 /* ---- transitive closure: replaces utils.ancestor (utils.py:37-54) as called by

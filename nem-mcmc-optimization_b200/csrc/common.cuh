@@ -8,6 +8,10 @@
 
 #define NEMB200_LOG2E 1.4426950408889634074
 #define NEMB200_LN2 0.69314718055994530942
+// multi-level table epilogue (score_tc.cu, EPI_LUTM): floats per level (n(n+1)/2 + p, n <= 118), number of levels
+#define NEMB200_LUTM_STRIDE 7168
+#define NEMB200_LUTM_LEVELS 3
+#define NEMB200_LUTM_MAX_S 118
 
 // ---- host handle ---------------------------------------------------------------------------
 struct nemb200_dataset {
@@ -28,6 +32,9 @@ struct nemb200_dataset {
   uint8_t *a_pair;    // operand image of the pair-merged kernel: 4*D, eight constant rows of 128 and one of 4
   int pair_ok;        // pair-merged table kernel usable (table valid, 33 <= S <= 52)
   float *tabs;        // compact exp table of the pair planner: tabs[n(n+1)/2 + p] = lut[n-p][p], n <= S
+  float *lutm;        // [levels][NEMB200_LUTM_STRIDE] multi-level compact exp table (64 <= S <= 118)
+  int lutm_levels;    // 0 = not usable for this dataset, else 1..3 levels cover the dynamic range
+  double lutm_scale[NEMB200_LUTM_LEVELS];  // scale of each level, highest first
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)
   double *sumN;       // [1] A * sum(D)   (nem.py:62 summed over e)
   int *counters;      // [64] self-resetting completion counters of the score kernel's fused finalize (zero at rest)

@@ -21,8 +21,11 @@ namespace {
 
 // pair-merged table kernel (score_tc.cu): 32 accumulator columns per graph, S + 9 K rows <= 64
 bool pair_supported(int S) { return S >= 33 && S <= 52; }
+// multi-level table kernel (score_tc.cu, EPI_LUTM): same operand image as the pair kernel, S + 9 K rows <= 128 and a
+// compact table of (S+1)(S+2)/2 <= kLutmStride entries per level
+bool lutm_supported(int S) { return S >= 64 && S <= NEMB200_LUTM_MAX_S; }
 
-struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, sumN, counters, total; int W, n_mtiles; };
+struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, lutm, sumN, counters, total; int W, n_mtiles; };
 Layout make_layout(int S, int E) {
   Layout L;
   L.W = (S + 31) / 32;
@@ -30,9 +33,10 @@ Layout make_layout(int S, int E) {
   size_t off = 0;
   L.dcol = off; off = align_up(off + (size_t)L.n_mtiles * 128 * L.W * 4, 1024);
   L.a_lut = off; off = align_up(off + (size_t)L.n_mtiles * 128 * 128, 1024);
-  L.a_pair = off; off = align_up(off + (pair_supported(S) ? (size_t)L.n_mtiles * 128 * 128 : 0), 1024);
+  L.a_pair = off; off = align_up(off + ((pair_supported(S) || lutm_supported(S)) ? (size_t)L.n_mtiles * 128 * 128 : 0), 1024);
   L.lut = off; off = align_up(off + 64 * 64 * 4, 1024);
   L.tabs = off; off = align_up(off + 65 * 66 / 2 * 4, 1024);
+  L.lutm = off; off = align_up(off + (lutm_supported(S) ? (size_t)NEMB200_LUTM_LEVELS * NEMB200_LUTM_STRIDE * 4 : 0), 1024);
   L.sumN = off; off = align_up(off + 8, 1024);
   L.counters = off; off = align_up(off + 64 * 4, 1024);
   L.total = off;
@@ -99,6 +103,25 @@ __global__ void k_build_lut(int S, double alpha2, double beta2, double s, float 
   if (n <= S && n < 64) tabs[n * (n + 1) / 2 + p] = v;  // compact copy for the pair planner
 }
 
+// multi-level compact table: level l, entry n(n+1)/2 + p = 2^(alpha2*p + beta2*(n-p) - s_l) (fp64 -> fp32: +inf where a
+// level overflows, 0 where it underflows; the epilogue never selects a level in either state, see score_tc.cu)
+__global__ void k_build_lutm(int S, double alpha2, double beta2, double s0, double s1, double s2, int levels, float *lutm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NEMB200_LUTM_STRIDE) return;
+  int n = 0;
+  while ((n + 1) * (n + 2) / 2 <= i) ++n;
+  const int p = i - n * (n + 1) / 2;
+  for (int l = 0; l < NEMB200_LUTM_LEVELS; ++l) {
+    const double s = l == 0 ? s0 : (l == 1 ? s1 : s2);
+    float v = 0.f;
+    if (n <= S && l < levels) {
+      const double x = alpha2 * p + beta2 * (n - p) - s;
+      v = x < -126.0 ? 0.f : (float)exp2(x);
+    }
+    lutm[(size_t)l * NEMB200_LUTM_STRIDE + i] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" size_t nemb200_dataset_bytes(int S, int E) {
@@ -146,7 +169,22 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
   k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 0, h->a_lut);
   h->pair_ok = h->lut_valid && pair_supported(S);
-  if (h->pair_ok) k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 1, h->a_pair);
+  // multi-level table epilogue (64 <= S <= 118): the null site bounds every E-gene's largest term from below by
+  // 2^0, so the levels only have to cover [0, vmax]: the lowest level has scale T-1, each further one sits
+  // `step` = 121 + T - 1 binary orders higher, and level 0 must hold vmax + log2(S+1) without overflow (T = 90 is
+  // the selection threshold of the epilogue: a level is used iff its sum is >= 2^-T)
+  h->lutm_levels = 0;
+  if (lutm_supported(S)) {
+    const double T = 90.0, step = 121.0 + T - 1.0, top = vmax + log2((double)S + 1.0);
+    for (int lv = 2; lv <= NEMB200_LUTM_LEVELS && h->lutm_levels == 0; ++lv)
+      if (top < (T - 1.0) + (lv - 1) * step + 127.0) h->lutm_levels = lv;
+    for (int l = 0; l < h->lutm_levels; ++l) h->lutm_scale[l] = (T - 1.0) + (h->lutm_levels - 1 - l) * step;
+  }
+  h->lutm = (float *)(base + L.lutm);
+  if (h->lutm_levels > 0)
+    k_build_lutm<<<(NEMB200_LUTM_STRIDE + 255) / 256, 256, 0, st>>>(S, h->alpha2, h->beta2, h->lutm_scale[0], h->lutm_scale[1],
+                                                                  h->lutm_scale[2], h->lutm_levels, h->lutm);
+  if (h->pair_ok || h->lutm_levels > 0) k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 1, h->a_pair);
   k_sumN<<<1, 256, 0, st>>>(h->dcol, (size_t)E_pad * L.W, A, h->sumN);
   k_build_lut<<<16, 256, 0, st>>>(S, h->alpha2, h->beta2, (double)h->scale, h->lut, h->tabs);
   cudaError_t e = cudaGetLastError();
@@ -172,5 +210,6 @@ extern "C" int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int
   NEMB_REQUIRE(h != nullptr && info != nullptr && n >= 8, "dataset_info needs a handle and 8 slots");
   info[0] = h->S; info[1] = h->E; info[2] = h->W; info[3] = 128; info[4] = h->lut_valid ? h->G_lut : h->G;
   info[5] = h->lut_valid; info[6] = h->scale; info[7] = h->n_mtiles;
+  if (n >= 9) info[8] = h->lutm_levels;
   return 0;
 }

@@ -55,22 +55,23 @@ constexpr int kPairCap = 1568;              // table entries per graph (planner 
 constexpr int kPairLim = 256;               // table entries per pair (keeps every B weight <= 128)
 constexpr int kPairZero = 2040;             // float index (in the single-site table region) of a permanent 0
 constexpr int kPlanColBytes = 80;           // planner output per accumulator column: 64 B-operand bytes + 16 bytes of meta
-template <bool PAIR>
+constexpr int kLutmStride = NEMB200_LUTM_STRIDE;  // floats per level of the multi-level table (n(n+1)/2 + p, n <= 118)
+template <bool PAIR, bool LUT3 = false>
 struct Lay {
-  static constexpr int STAGES = PAIR ? 3 : 4;
+  static constexpr int STAGES = (PAIR || LUT3) ? 3 : 4;
   static constexpr int LUT = 0;                                   // standard kernel: base must be < 32 KB and 128-aligned
-  static constexpr int LUT_BYTES = PAIR ? 8192 : kLutBytes;
+  static constexpr int LUT_BYTES = LUT3 ? NEMB200_LUTM_LEVELS * kLutmStride * 4 : (PAIR ? 8192 : kLutBytes);
   static constexpr int B = LUT + LUT_BYTES;                       // 2 buffers x (256 x 128 B)
   static constexpr int A = B + 2 * 2 * kTileBytes;                // STAGES x 16 KB
   static constexpr int BIAS = A + STAGES * kTileBytes;            // 2 buffers x 1024 floats (ex2 epilogues)
-  static constexpr int ROWS = BIAS + (PAIR ? 0 : 2 * 1024 * 4);   // 1024 words of bit rows (+ 512 words of scan scratch)
+  static constexpr int ROWS = BIAS + ((PAIR || LUT3) ? 0 : 2 * 1024 * 4);   // 1024 words of bit rows (+ 512 words of scan scratch)
   static constexpr int RED = ROWS + 1024 * 4 + (PAIR ? 2048 : 0); // 20 warps x 8 doubles
   static constexpr int BAR = RED + 20 * 8 * 8;                    // barriers + scalars
   static constexpr int TAB = BAR + 256;                           // PAIR: 2 buffers of pair tables
   static constexpr int TAB_BYTES = PAIR ? kPairG * kPairCap * 4 : 0;
   static constexpr int BYTES = TAB + 2 * TAB_BYTES;
 };
-static_assert(Lay<true>::BYTES <= 232448 && Lay<false>::BYTES <= 232448, "shared memory budget");
+static_assert(Lay<true>::BYTES <= 232448 && Lay<false>::BYTES <= 232448 && Lay<false, true>::BYTES <= 232448, "shared memory budget");
 
 struct Params {
   const uint32_t *phi;   // [n_graphs][S][W]
@@ -82,6 +83,7 @@ struct Params {
   float k1;              // EX2: x = k1 * acc + bias_j
   float kc;              // EX2: bias_j = kc * c_j - s
   float scale;           // s
+  float lvl_scale[3];    // EPI_LUTM: scale of each table level, highest first
   // pair kernel: per graph kPairCS columns of (site, partner or 255); 255,255 = padding column
   const uint8_t *plan;
   const float *tables;   // pair kernel: per graph kPairCap floats (the graph's pair tables, built by the planner)
@@ -183,6 +185,12 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+template <int OFF>
+__device__ __forceinline__ float lds_f32_off(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
 __device__ __forceinline__ float ex2f(float x) {
   float v;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(x));
@@ -197,7 +205,7 @@ __device__ __forceinline__ float log2_split(float x) {
   return (float)e + l;
 }
 
-enum { EPI_LUT = 0, EPI_EX2 = 1, EPI_EX2_2PASS = 2 };
+enum { EPI_LUT = 0, EPI_EX2 = 1, EPI_EX2_2PASS = 2, EPI_LUTM = 3 };
 
 // Named barrier of one epilogue warpgroup (ids 1..5).  The id is an immediate on purpose: with a register operand
 // ptxas reserves all 16 hardware barriers for the kernel, and then no CTA that uses __syncthreads() (the MCMC accept
@@ -310,15 +318,50 @@ __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *
   return log2_split(ex2f(-p.scale) + acc0 + acc1) + p.scale;
 }
 
-template <int EPI>
+// ---- multi-level table epilogue (EPI_LUTM, 64 <= S <= 118, NLEV = 2 or 3 levels): a site's term is
+// V(n_j, p) = 2^(x - s_l) with n_j = |ancestors-or-self of j| known per column and p the count of ones among them, so
+// the accumulator is made the shared-memory address of entry n_j(n_j+1)/2 + p of the level-0 table; the same entry at
+// the lower scales sits kLutmStride floats further each.  One site costs NLEV look-ups and no exponential.  A single
+// scale cannot hold the terms (x spans > 700 binary orders at S = 100), but the null site bounds every E-gene's
+// largest term from below by 2^0, and the scales (dataset.cu) are spaced so that the FIRST level whose sum reaches
+// 2^-90 has neither overflowed nor lost a term within 2^-22 of the sum; the last level always qualifies (it holds
+// the null term 2^-89).  Returns log2(1 + sum_j 2^x_j).
+template <int NLEV>
+__device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int S, const Params &p) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int c = 0; c < S; c += 16) {
+    const int cs = min(c, S - 16), skip = c - cs;  // the last chunk is shifted back so it never over-reads
+    uint32_t r[16];
+    TMEM_LD16(taddr + cs, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v0 = lds_f32(r[i]), v1 = lds_f32_off<kLutmStride * 4>(r[i]);
+      float v2 = 0.f;
+      if (NLEV > 2) v2 = lds_f32_off<2 * kLutmStride * 4>(r[i]);
+      if (i >= skip) { a0 += v0; a1 += v1; a2 += v2; }
+    }
+  }
+  // null site x = 0 at each level (flushes to zero where it is far below the level's range)
+  a0 += ex2f(-p.lvl_scale[0]); a1 += ex2f(-p.lvl_scale[1]);
+  if (NLEV > 2) a2 += ex2f(-p.lvl_scale[2]);
+  const float lo = 8.077935669463161e-28f;  // 2^-90
+  if (a0 >= lo) return log2_split(a0) + p.lvl_scale[0];
+  if (NLEV == 2 || a1 >= lo) return log2_split(a1) + p.lvl_scale[1];
+  return log2_split(a2) + p.lvl_scale[2];
+}
+
+template <int EPI, int NLEV>
 __device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const float *sBias, const Params &p, bool valid,
                                                       int ng_mine, double (&part)[kMaxG / 4]) {
   const int S = p.S, bstride = kBiasStride * (S > 64 ? 2 : 1);
 #pragma unroll
   for (int g = 0; g < kMaxG / 4; ++g) {
     if (g < ng_mine) {
-      float l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * p.CS, S, sBias + g * bstride, p)
-                        : graph_lse2<EPI, 8>(taddr + g * p.CS, S, sBias + g * bstride, p);
+      float l;
+      if constexpr (EPI == EPI_LUTM) l = graph_lse_levels<NLEV>(taddr + g * p.CS, S, p);
+      else l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * p.CS, S, sBias + g * bstride, p)
+                       : graph_lse2<EPI, 8>(taddr + g * p.CS, S, sBias + g * bstride, p);
       if (valid) part[g] += (double)l;
     }
   }
@@ -456,7 +499,7 @@ __device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem
 template <int EPI, int S_T, int NLUT, bool PAIR = false>
 __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p) {
   constexpr int NWG = S_T > 0 ? epi_warpgroups(S_T) : 4;
-  using L = Lay<PAIR>;
+  using L = Lay<PAIR, EPI == EPI_LUTM>;
   constexpr int kStages = L::STAGES;
   static_assert(!PAIR || (EPI == EPI_LUT && S_T == kPairCS), "the pair kernel is the 32-column table kernel");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -494,6 +537,8 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     }
   } else if (EPI == EPI_LUT) {
     for (int i = threadIdx.x; i < kLutBytes / 4; i += cta_threads(S_T)) reinterpret_cast<float *>(smem + L::LUT)[i] = p.lut[i];
+  } else if (EPI == EPI_LUTM) {  // NLUT = number of table levels
+    for (int i = threadIdx.x; i < NLUT * kLutmStride; i += cta_threads(S_T)) reinterpret_cast<float *>(smem + L::LUT)[i] = p.lut[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -518,8 +563,8 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     }
     sync();
     uint8_t *brow = smem + L::B + bb * 2 * kTileBytes;
-    float *bias = reinterpret_cast<float *>(smem + L::BIAS) + bb * 1024;
-    const int bstride = kBiasStride * (S > 64 ? 2 : 1);
+    [[maybe_unused]] float *bias = reinterpret_cast<float *>(smem + L::BIAS) + bb * 1024;
+    [[maybe_unused]] const int bstride = kBiasStride * (S > 64 ? 2 : 1);
     const int CS = p.CS;
     // padding sites (S <= j < CS) of the specialised kernels look up a table entry that is zero:
     // offset 128*m with m odd is entry [q=(m-1)/2][p=32], zero as soon as 32 + (m-1)/2 > S
@@ -546,10 +591,11 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       for (int c = 0; c < 8; ++c) {
         uint32_t half = (anc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
         uint4 v;
-        v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-        v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-        v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
-        v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << 1;
+        constexpr int sh = EPI == EPI_LUTM ? 0 : 1;  // operand value 2 (the A operand tells D=1 from D=0); LUTM: 1 (A = 4*D)
+        v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
+        v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
+        v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
+        v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
         if (lut_site && c == (S >> 4)) {
           uint32_t extv = ((sbase + L::LUT) >> 7) + (j >= S ? zero_m : 0u);
           if (extv > 255u) asm volatile("trap;");  // the table must sit in the first 32 KB of shared memory
@@ -559,7 +605,16 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
         }
         *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
       }
-      if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
+      if constexpr (EPI == EPI_LUTM) {
+        // constant K rows (A operand: 128 in row S, 4 in row S+8): the byte address of the column's first table entry,
+        // V(n_j, 0) of level 0; unused columns point at the table base
+        const uint32_t addr = sbase + L::LUT + 4u * (uint32_t)(used ? cnt * (cnt + 1) / 2 : 0);
+        if ((addr >> 7) > 255u) asm volatile("trap;");  // level 0 must sit in the first 32 KB of shared memory
+        brow[sw128((uint32_t)col, (uint32_t)S)] = (uint8_t)(addr >> 7);
+        brow[sw128((uint32_t)col, (uint32_t)(S + 8))] = (uint8_t)((addr & 127u) >> 2);
+      } else {
+        if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   };
@@ -731,7 +786,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
           if (ng_mine > 0 && !DBG(1)) {
             const uint32_t taddr = tmem_base + buf * 256u + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16);
             const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
-            tile_epilogue_generic<EPI>(taddr, bias, p, valid, ng_mine, part);
+            tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part);
           }
           tc_fence_before();
           __syncwarp();
@@ -1071,7 +1126,10 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   // AUTO never picks the pair-merged kernel: its score kernel is faster (76 vs 103 us at S=50, E=10k, 1024 graphs)
   // but the per-graph planner costs what it saves (about 20 us per 1024 graphs); callers opt in with TC_PAIR
   if (impl == NEMB200_SCORE_AUTO)
-    impl = h->lut_valid ? NEMB200_SCORE_TC_LUT : (h->fixed_valid ? NEMB200_SCORE_TC_EX2 : NEMB200_SCORE_TC_EX2_2PASS);
+    impl = h->lut_valid ? NEMB200_SCORE_TC_LUT
+                        : (h->fixed_valid ? NEMB200_SCORE_TC_EX2 : (h->lutm_levels > 0 ? NEMB200_SCORE_TC_LUTM : NEMB200_SCORE_TC_EX2_2PASS));
+  NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUTM || h->lutm_levels > 0,
+               "multi-level table epilogue not available for this dataset (needs 64 <= S <= %d, S=%d)", NEMB200_LUTM_MAX_S, h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_PAIR || h->pair_ok, "pair-merged table epilogue not available for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUT || h->lut_valid, "exp-table epilogue not valid for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_EX2 || h->fixed_valid, "fixed-scale ex2 epilogue not valid for this dataset");
@@ -1084,6 +1142,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   const int nsm = num_sms() - leave_sms_free > 8 ? num_sms() - leave_sms_free : num_sms();
   const bool pair = impl == NEMB200_SCORE_TC_PAIR;
   const bool lut = impl == NEMB200_SCORE_TC_LUT;
+  const bool lutm = impl == NEMB200_SCORE_TC_LUTM;
   const int G = pair ? kPairG : (lut ? h->G_lut : h->G);  // graphs per MMA N tile of the kernel that will run
   const int CS = pair ? kPairCS : h->CS;
   const WsLay wl = ws_layout(h, n, pair);
@@ -1093,13 +1152,14 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
                "batch too large for one launch (%d graphs x %d E tiles): split it", n, h->n_mtiles);
   const unsigned T = (unsigned)n_ntiles * (unsigned)h->n_mtiles;
   Params p;
-  p.phi = phi; p.a_img = pair ? h->a_pair : h->a_lut; p.lut = h->lut;
+  p.phi = phi; p.a_img = (pair || lutm) ? h->a_pair : h->a_lut; p.lut = lutm ? h->lutm : h->lut;
+  for (int l = 0; l < 3; ++l) p.lvl_scale[l] = (float)h->lutm_scale[l];
   p.partials = reinterpret_cast<double *>(wb + wl.partials);
   p.n_graphs = n; p.S = h->S; p.W = h->W; p.E = h->E; p.G = G;
   p.n_mtiles = h->n_mtiles; p.n_slots = kMaxSlots;
   p.CS = CS;
   p.nmma = (G * CS + 15) / 16 * 16;
-  p.ksteps = pair ? (h->S + 9 + 31) / 32 : (h->S + (lut ? 1 : 0) + 31) / 32;
+  p.ksteps = (pair || lutm) ? (h->S + 9 + 31) / 32 : (h->S + (lut ? 1 : 0) + 31) / 32;
   // accumulator a = 4p + 256q = 256c - 252p  ->  x = alpha2*p + beta2*q = k1*a + kc*c
   const double kappa2 = h->alpha2 - h->beta2;
   p.k1 = (float)(-kappa2 / 252.0);
@@ -1146,6 +1206,9 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
     fbslot = fslot;
   } else if (lut) {
     rc = launch_lut(h, p, grid, st);
+  } else if (lutm) {
+    rc = h->lutm_levels == 2 ? launch_kernel(k_score_tc<EPI_LUTM, 0, 2>, p, grid, cta_threads(0), st, Lay<false, true>::BYTES)
+                             : launch_kernel(k_score_tc<EPI_LUTM, 0, 3>, p, grid, cta_threads(0), st, Lay<false, true>::BYTES);
   } else if (impl == NEMB200_SCORE_TC_EX2) {
     rc = launch_kernel(k_score_tc<EPI_EX2, 0, 0>, p, grid, cta_threads(0), st);
   } else if (impl == NEMB200_SCORE_TC_EX2_2PASS) {

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 
 RULE_FULL, RULE_MASKED = 0, 1
-SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5, "pair": 6}
+SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5, "pair": 6, "lutm": 7}
 
 
 def _require_cuda(device=None) -> torch.device:
@@ -155,10 +155,11 @@ class Dataset:
                                             nbytes, _stream_ptr(st), C.byref(h)))
         self._h = h
         st.synchronize()  # d (the uint8 copy) may be freed after this
-        info = (C.c_int64 * 8)()
-        _lib.check(L.nemb200_dataset_info(self._h, info, 8))
+        info = (C.c_int64 * 9)()
+        _lib.check(L.nemb200_dataset_info(self._h, info, 9))
         self.W, self.graphs_per_tile, self.lut_valid, self.scale_log2, self.n_mtiles = (
             int(info[2]), int(info[4]), bool(info[5]), int(info[6]), int(info[7]))
+        self.lutm_levels = int(info[8])  # levels of the multi-level exp table (64 <= S <= 118), 0 = not usable
         self._score_ws = None
 
     def __del__(self):

@@ -143,8 +143,8 @@ def test_score_noise_free_small_score(nb, golden):
 
 
 @pytest.mark.parametrize("S,E,n", [(8, 40, 7), (10, 100, 33), (16, 257, 17), (20, 1000, 64), (30, 5000, 41),
-                                   (50, 1000, 23), (50, 10000, 12), (63, 700, 9), (64, 300, 9), (100, 1500, 7),
-                                   (128, 260, 5)])
+                                   (50, 1000, 23), (50, 10000, 12), (63, 700, 9), (64, 300, 9), (77, 900, 11),
+                                   (100, 1500, 7), (118, 640, 6), (119, 200, 4), (128, 260, 5)])
 def test_score_synthetic_vs_oracle(nb, S, E, n):
     rng = np.random.default_rng(S * 1000 + E)
     _, _, D = orc.synth_dataset(S, E, seed=S + E)
@@ -157,6 +157,9 @@ def test_score_synthetic_vs_oracle(nb, S, E, n):
     assert np.allclose(ds.score_graphs(graphs, impl="witness"), ref, rtol=REL_WITNESS)
     impls = [i for i in TC_IMPLS if (i != "lut" or ds.lut_valid) and (i != "ex2" or S <= 54)]
     assert impls
+    assert (ds.lutm_levels > 0) == (64 <= S <= 118)
+    if ds.lutm_levels:
+        impls.append("lutm")
     for impl in impls:
         got = ds.score_graphs(graphs, impl=impl)
         assert np.allclose(got, ref, rtol=REL_TC), (impl, np.abs(got / ref - 1).max())
@@ -194,6 +197,41 @@ def test_score_other_error_rates_and_unsupported(nb):
     ds = nb.Dataset(np.zeros((100, 10), dtype=np.uint8), *orc.nem_constants(0.05, 0.1))
     with pytest.raises(nb._lib.NemB200Error):
         ds.score_graphs(np.zeros((1, 100, 100), dtype=np.uint8), impl="lut")   # table epilogue needs S <= 63
+
+
+@pytest.mark.parametrize("S", [64, 100, 118])
+def test_score_multilevel_table_extremes(nb, S):
+    """Multi-level table epilogue (csrc/score_tc.cu: graph_lse_levels): every E-gene's terms span hundreds of binary
+    orders, and which level is used depends on the E-gene.  Extreme data (all ones: the largest possible terms, all
+    zeros: every term below the null site, one-hot rows) x extreme graphs (empty, complete order, all ones), and
+    error rates that need two or three levels or rule the table out."""
+    rng = np.random.default_rng(S)
+    E = 517
+    D = (rng.random((S, E)) < 0.5).astype(np.uint8)
+    D[:, :64] = 1; D[:, 64:128] = 0
+    D[:, 128:192] = (rng.random((S, 64)) < 0.95); D[:, 192:256] = (rng.random((S, 64)) < 0.05)
+    D[:, 256:256 + S] = np.eye(S, dtype=np.uint8)[:, :min(S, E - 256)]
+    graphs = np.concatenate([rand_dags(rng, 9, S, p=0.3), rand_dags(rng, 4, S, p=0.02),
+                             np.stack([orc.order_to_graph(rng.permutation(S)) for _ in range(3)]).astype(np.uint8),
+                             np.zeros((1, S, S), dtype=np.uint8), np.ones((1, S, S), dtype=np.uint8)])
+    seen = set()
+    for alpha, beta in [(0.05, 0.1), (0.02, 0.1), (0.01, 0.01), (0.2, 0.3), (0.45, 0.001), (0.6, 0.7)]:
+        A, B = orc.nem_constants(alpha, beta)
+        ds = nb.Dataset(D, A, B)
+        w = ds.score_graphs(graphs, impl="witness")
+        seen.add(ds.lutm_levels)
+        if ds.lutm_levels == 0:
+            with pytest.raises(nb._lib.NemB200Error):
+                ds.score_graphs(graphs, impl="lutm")
+        else:
+            got = ds.score_graphs(graphs, impl="lutm")
+            assert np.allclose(got, w, rtol=REL_TC), (alpha, beta, ds.lutm_levels, np.abs(got / w - 1).max())
+            for k in (1, 3):                                               # partial N tiles
+                assert np.array_equal(ds.score_graphs(graphs[:k], impl="lutm"), got[:k])
+        assert np.allclose(ds.score_graphs(graphs), w, rtol=REL_TC)       # auto, whatever it picks
+        ref = c_oracle.score_batch(graphs[:3], D, A, B, nthreads=3)
+        assert np.allclose(w[:3], ref, rtol=REL_WITNESS)
+    assert {2, 3} <= seen, seen
 
 
 @pytest.mark.parametrize("S", [33, 40, 47, 50, 52])
@@ -261,8 +299,10 @@ def test_score_config4_shape_vs_witness(nb):
     orders = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
     bits = ds.order_graphs(orders, rule=1, cand=cand, use_nem=True)
     w = ds.score_bits(bits, impl="witness").cpu().numpy()
-    got = ds.score_bits(bits).cpu().numpy()
-    assert np.allclose(got, w, rtol=REL_TC), np.abs(got / w - 1).max()
+    assert ds.lutm_levels == 2                                         # auto = the two-level table epilogue
+    for impl in ("auto", "lutm", "ex2_2pass"):
+        got = ds.score_bits(bits, impl=impl).cpu().numpy()
+        assert np.allclose(got, w, rtol=REL_TC), (impl, np.abs(got / w - 1).max())
     graphs = nb.unpack_adj(bits[:2].cpu().numpy().view(np.uint32), S)
     assert np.allclose(w[:2], c_oracle.score_batch(graphs, D, A, B, nthreads=2), rtol=REL_WITNESS)
 
