@@ -12,6 +12,7 @@
 #define NEMB200_LUTM_STRIDE 7168
 #define NEMB200_LUTM_LEVELS 3
 #define NEMB200_LUTM_MAX_S 118
+#define NEMB200_LUTM_ZERO 7160   // entry that is 0 at every level (n = 119 > S): what padding columns look up
 
 // ---- host handle ---------------------------------------------------------------------------
 struct nemb200_dataset {
@@ -33,6 +34,7 @@ struct nemb200_dataset {
   int pair_ok;        // pair-merged table kernel usable (table valid, 33 <= S <= 52)
   float *tabs;        // compact exp table of the pair planner: tabs[n(n+1)/2 + p] = lut[n-p][p], n <= S
   float *lutm;        // [levels][NEMB200_LUTM_STRIDE] multi-level compact exp table (64 <= S <= 118)
+  int CS_lutm;        // accumulator columns per graph of the multi-level table kernel: S rounded up to a multiple of 8
   int lutm_levels;    // 0 = not usable for this dataset, else 1..3 levels cover the dynamic range
   double lutm_scale[NEMB200_LUTM_LEVELS];  // scale of each level, highest first
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)

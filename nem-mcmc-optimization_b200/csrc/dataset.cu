@@ -174,6 +174,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   // `step` = 121 + T - 1 binary orders higher, and level 0 must hold vmax + log2(S+1) without overflow (T = 90 is
   // the selection threshold of the epilogue: a level is used iff its sum is >= 2^-T)
   h->lutm_levels = 0;
+  h->CS_lutm = (S + 7) / 8 * 8;  // same graphs per tile as h->G: 4 at S = 64, else 2
   if (lutm_supported(S)) {
     const double T = 90.0, step = 121.0 + T - 1.0, top = vmax + log2((double)S + 1.0);
     for (int lv = 2; lv <= NEMB200_LUTM_LEVELS && h->lutm_levels == 0; ++lv)

@@ -64,7 +64,8 @@ struct Lay {
   static constexpr int B = LUT + LUT_BYTES;                       // 2 buffers x (256 x 128 B)
   static constexpr int A = B + 2 * 2 * kTileBytes;                // STAGES x 16 KB
   static constexpr int BIAS = A + STAGES * kTileBytes;            // 2 buffers x 1024 floats (ex2 epilogues)
-  static constexpr int ROWS = BIAS + ((PAIR || LUT3) ? 0 : 2 * 1024 * 4);   // 1024 words of bit rows (+ 512 words of scan scratch)
+  // (multi-level table kernel: the same region holds the level sums two warpgroups exchange, [slot 2][pair 2][3][128] floats)
+  static constexpr int ROWS = BIAS + (PAIR ? 0 : (LUT3 ? 2 * 2 * 3 * 128 * 4 : 2 * 1024 * 4));   // 1024 words of bit rows (+ 512 words of scan scratch)
   static constexpr int RED = ROWS + 1024 * 4 + (PAIR ? 2048 : 0); // 20 warps x 8 doubles
   static constexpr int BAR = RED + 20 * 8 * 8;                    // barriers + scalars
   static constexpr int TAB = BAR + 256;                           // PAIR: 2 buffers of pair tables
@@ -326,22 +327,37 @@ __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *
 // largest term from below by 2^0, and the scales (dataset.cu) are spaced so that the FIRST level whose sum reaches
 // 2^-90 has neither overflowed nor lost a term within 2^-22 of the sum; the last level always qualifies (it holds
 // the null term 2^-89).  Returns log2(1 + sum_j 2^x_j).
-template <int NLEV>
-__device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int S, const Params &p) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int c = 0; c < S; c += 16) {
-    const int cs = min(c, S - 16), skip = c - cs;  // the last chunk is shifted back so it never over-reads
-    uint32_t r[16];
-    TMEM_LD16(taddr + cs, r);
-    tmem_wait_ld();
+template <int NLEV, int N>
+__device__ __forceinline__ void level_add(const uint32_t (&r)[N], float &a0, float &a1, float &a2) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float v0 = lds_f32(r[i]), v1 = lds_f32_off<kLutmStride * 4>(r[i]);
-      float v2 = 0.f;
-      if (NLEV > 2) v2 = lds_f32_off<2 * kLutmStride * 4>(r[i]);
-      if (i >= skip) { a0 += v0; a1 += v1; a2 += v2; }
-    }
+  for (int i = 0; i < N; ++i) {
+    a0 += lds_f32(r[i]);
+    a1 += lds_f32_off<kLutmStride * 4>(r[i]);
+    if (NLEV > 2) a2 += lds_f32_off<2 * kLutmStride * 4>(r[i]);
   }
+}
+// columns [0, n), n a multiple of 8 (padding columns look up an entry that is zero at every level, so nothing in
+// here is predicated: the first version spent more issue slots on ISETP/FSEL than on look-ups).  Keeping the TMEM
+// load of the next chunk in flight during this chunk's look-ups was measured slower.
+template <int NLEV>
+__device__ __forceinline__ void level_sums(uint32_t taddr, int n, float &a0, float &a1, float &a2) {
+  a0 = 0.f; a1 = 0.f; a2 = 0.f;
+  int c = 0;
+  for (; c + 16 <= n; c += 16) {
+    uint32_t r[16];
+    TMEM_LD16(taddr + c, r);
+    tmem_wait_ld();
+    level_add<NLEV, 16>(r, a0, a1, a2);
+  }
+  if (c < n) {  // warp-uniform
+    uint32_t r[8];
+    TMEM_LD8(taddr + c, r);
+    tmem_wait_ld();
+    level_add<NLEV, 8>(r, a0, a1, a2);
+  }
+}
+template <int NLEV>
+__device__ __forceinline__ float levels_log(float a0, float a1, float a2, const Params &p) {
   // null site x = 0 at each level (flushes to zero where it is far below the level's range)
   a0 += ex2f(-p.lvl_scale[0]); a1 += ex2f(-p.lvl_scale[1]);
   if (NLEV > 2) a2 += ex2f(-p.lvl_scale[2]);
@@ -349,6 +365,31 @@ __device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int S, const P
   if (a0 >= lo) return log2_split(a0) + p.lvl_scale[0];
   if (NLEV == 2 || a1 >= lo) return log2_split(a1) + p.lvl_scale[1];
   return log2_split(a2) + p.lvl_scale[2];
+}
+template <int NLEV>
+__device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int n_cols, const Params &p) {
+  float a0, a1, a2;
+  level_sums<NLEV>(taddr, n_cols, a0, a1, a2);
+  return levels_log<NLEV>(a0, a1, a2, p);
+}
+// Two graphs per tile (S > 64) would leave two of the four epilogue warpgroups idle: instead warpgroups 2h and 2h+1
+// share graph h, each sums the table entries of one half of its sites, and the odd one hands its level sums to
+// the even one through shared memory (slot = tile parity; a 256-thread named barrier per tile).  The accumulator
+// hand-back (t_empty counts all 16 warps) keeps the odd warpgroup from running two tiles ahead, so two slots suffice.
+template <int NLEV>
+__device__ __forceinline__ void tile_epilogue_split(uint32_t taddr_graph, const Params &p, bool valid, int half, int pair,
+                                                    float *xch, int tw, double &part0) {
+  const int Sh = ((p.CS + 15) >> 4) << 3;  // both halves are multiples of 8 columns
+  float a0, a1, a2;
+  level_sums<NLEV>(taddr_graph + (half ? Sh : 0), half ? p.CS - Sh : Sh, a0, a1, a2);
+  if (half) { xch[tw] = a0; xch[128 + tw] = a1; if (NLEV > 2) xch[256 + tw] = a2; }
+  if (pair == 0) asm volatile("bar.sync 8, 256;" ::: "memory"); else asm volatile("bar.sync 9, 256;" ::: "memory");
+  if (!half) {
+    a0 += xch[tw]; a1 += xch[128 + tw];
+    if (NLEV > 2) a2 += xch[256 + tw];
+    const float l = levels_log<NLEV>(a0, a1, a2, p);
+    if (valid) part0 += (double)l;
+  }
 }
 
 template <int EPI, int NLEV>
@@ -359,7 +400,7 @@ __device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const floa
   for (int g = 0; g < kMaxG / 4; ++g) {
     if (g < ng_mine) {
       float l;
-      if constexpr (EPI == EPI_LUTM) l = graph_lse_levels<NLEV>(taddr + g * p.CS, S, p);
+      if constexpr (EPI == EPI_LUTM) l = graph_lse_levels<NLEV>(taddr + g * p.CS, p.CS, p);
       else l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * p.CS, S, sBias + g * bstride, p)
                        : graph_lse2<EPI, 8>(taddr + g * p.CS, S, sBias + g * bstride, p);
       if (valid) part[g] += (double)l;
@@ -607,8 +648,8 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       }
       if constexpr (EPI == EPI_LUTM) {
         // constant K rows (A operand: 128 in row S, 4 in row S+8): the byte address of the column's first table entry,
-        // V(n_j, 0) of level 0; unused columns point at the table base
-        const uint32_t addr = sbase + L::LUT + 4u * (uint32_t)(used ? cnt * (cnt + 1) / 2 : 0);
+        // V(n_j, 0) of level 0; padding columns and absent graphs look up an entry that is zero at every level
+        const uint32_t addr = sbase + L::LUT + 4u * (uint32_t)(used ? cnt * (cnt + 1) / 2 : NEMB200_LUTM_ZERO);
         if ((addr >> 7) > 255u) asm volatile("trap;");  // level 0 must sit in the first 32 KB of shared memory
         brow[sw128((uint32_t)col, (uint32_t)S)] = (uint8_t)(addr >> 7);
         brow[sw128((uint32_t)col, (uint32_t)(S + 8))] = (uint8_t)((addr & 127u) >> 2);
@@ -758,13 +799,14 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     // =============================== epilogue: 4 warpgroups share every tile, a quarter of its graphs each ===
     const int wg = (warp - 4) >> 2, quarter = warp & 3, tw = threadIdx.x - 128 - wg * 128;
     const int gq = G >= NWG ? G / NWG : 1;                       // graphs per warpgroup (G == 2: warpgroups 2,3 idle)
+    const bool split = EPI == EPI_LUTM && G == 2;                // ... unless two warpgroups share a graph (tile_epilogue_split)
     const int bstride = kBiasStride * (S > 64 ? 2 : 1);
     uint32_t it = 0;
     Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
     Item im;
     for (int k = 0; wk.next(im, p.n_mtiles); ++k) {
       const int ntile = im.ntile, m0 = im.m0, nt = im.nt;
-      const int gl = wg * gq;                                     // first graph (within the tile) of this warpgroup
+      const int gl = split ? (wg >> 1) : wg * gq;                 // first graph (within the tile) of this warpgroup
       const int g0 = ntile * G + gl;
       const int ng_mine = gl < G ? max(0, min(gq, n_graphs - g0)) : 0;
       const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
@@ -786,7 +828,15 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
           if (ng_mine > 0 && !DBG(1)) {
             const uint32_t taddr = tmem_base + buf * 256u + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16);
             const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
-            tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part);
+            if constexpr (EPI == EPI_LUTM) {
+              if (split)
+                tile_epilogue_split<NLUT>(taddr, p, valid, wg & 1, wg >> 1,
+                                          reinterpret_cast<float *>(smem + L::BIAS) + ((buf * 2 + (wg >> 1)) * 3) * 128, tw, part[0]);
+              else
+                tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part);
+            } else {
+              tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part);
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -794,9 +844,10 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
         }
       }
       // ---- per-item reduction inside the warpgroup -> one double per (graph, chunk)
+      const int ng_out = (split && (wg & 1)) ? 0 : ng_mine;  // the odd warpgroup of a pair only helps
 #pragma unroll
       for (int g = 0; g < kMaxG / 4; ++g) {
-        if (g < ng_mine) {
+        if (g < ng_out) {
           double v = part[g];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -806,7 +857,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_edone + 8 * bb);  // bias / B buffer of this item may be recycled
       wg_bar_sync(wg);
-      if (tw < ng_mine) {
+      if (tw < ng_out) {
         double v = 0.0;
         for (int w4 = 0; w4 < 4; ++w4) v += sRed[(wg * 4 + w4) * 8 + tw];
         p.partials[(size_t)(g0 + tw) * p.n_slots + item_slot(ntile, n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x)] = v;  // list mode: indexed by list position
@@ -1144,7 +1195,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   const bool lut = impl == NEMB200_SCORE_TC_LUT;
   const bool lutm = impl == NEMB200_SCORE_TC_LUTM;
   const int G = pair ? kPairG : (lut ? h->G_lut : h->G);  // graphs per MMA N tile of the kernel that will run
-  const int CS = pair ? kPairCS : h->CS;
+  const int CS = pair ? kPairCS : (lutm ? h->CS_lutm : h->CS);
   const WsLay wl = ws_layout(h, n, pair);
   uint8_t *wb = reinterpret_cast<uint8_t *>(ws);
   const int n_ntiles = (n + G - 1) / G;
