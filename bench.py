@@ -175,6 +175,40 @@ def edge_fit_leg(nb, synth, with_cpu):
     return row
 
 
+def config4_shape_leg(nb, synth):
+    """BASELINE config 4 shape on ONE GPU: S=100 x E=100 000, the 512 chains one GPU of eight gets.  Score kernel alone
+    (multi-level table epilogue, and the max-subtracted ex2 epilogue it replaced) and the device-resident MCMC loop."""
+    import torch
+    s, e, n = 100, 100000, 512
+    adj, _, _ = synth.dataset(s, 8, seed=0, alpha=ALPHA, beta=BETA)      # true graph only; data synthesised on the device
+    ends = np.random.default_rng(0).integers(0, s, size=e)
+    D = synth.device_knockdown(adj, ends, ALPHA, BETA, seed=0)
+    ds = nb.Dataset(D, *synth.nem_constants(ALPHA, BETA), sort_egenes=True)  # conflict-free table look-ups
+    cand = (np.random.default_rng(7).random((s, s)) < 0.2).astype(np.uint8)
+    orders = synth.random_orders(n, s, seed=5)
+    bits = ds.order_graphs(orders, rule=nb.RULE_MASKED, cand=cand, use_nem=True)
+    row = {"config": "S=100 E=100000, 512 graphs / chains (one GPU's share of config 4)", "lutm_levels": ds.lutm_levels}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for impl in ("lutm", "ex2_2pass"):
+        for _ in range(2):
+            ds.score_bits(bits, impl=impl)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(5):
+            ds.score_bits(bits, impl=impl)
+        ev1.record(); torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 5
+        row[f"score_{impl}_ms"] = ms
+        row[f"score_{impl}_tflops_algorithmic"] = 2.0 * s * s * e * n / (ms * 1e-3) / 1e12
+    st = nb.ChainState(ds, orders, 2.0 * s / e, edge_counts=True, seed=1234, rule=nb.RULE_MASKED, cand=cand, use_nem=True)
+    st.run(32)
+    torch.cuda.synchronize()
+    ev0.record(); st.run(32); ev1.record(); torch.cuda.synchronize()
+    row["mcmc_ms_per_iter"] = ev0.elapsed_time(ev1) / 32
+    row["mcmc_chain_iterations_per_s"] = n * 32 / (ev0.elapsed_time(ev1) * 1e-3)
+    return row
+
+
 def config5_sweep(nb, synth):
     """BASELINE config 5: 65 536 random DAGs, S=30 x E=5000: closure + score throughput, bit rows resident."""
     import torch
@@ -424,6 +458,8 @@ def run_gpu(args, rank, world, local_rank):
             out["edge_fit"] = edge_fit_leg(nb, synth, not args.no_cpu)
             out["mcmc_small"] = small_mcmc_configs(nb, synth, not args.no_cpu)
             out["sweep_config5"] = config5_sweep(nb, synth)
+            if "config4" not in os.environ.get("BENCH_SKIP", ""):
+                out["config4_shape"] = config4_shape_leg(nb, synth)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             v0, _ = cpu_arm(D, A, B, unclosed_graphs(2 * cores, 2), cores)   # rate estimate

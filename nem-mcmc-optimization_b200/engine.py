@@ -132,8 +132,14 @@ class Dataset:
                 D = D.detach().cpu().numpy()
             d_host = np.ascontiguousarray((np.asarray(D) != 0).astype(np.uint8))
             if sort_egenes and d_host.shape[1] > 1:
-                # number of ones first (it bounds every count p), then the pattern itself
-                keys = [d_host[i] for i in range(d_host.shape[0] - 1, -1, -1)] + [d_host.sum(axis=0)]
+                # number of ones first (it bounds every count p), then the pattern itself (row 0 most significant);
+                # the pattern is compared as big-endian 64-bit words: S/64 sort keys instead of S
+                packed = np.packbits(d_host, axis=0)                                  # row 0 = MSB of byte 0
+                pad = (-packed.shape[0]) % 8
+                if pad:
+                    packed = np.concatenate([packed, np.zeros((pad, packed.shape[1]), dtype=np.uint8)])
+                words = np.ascontiguousarray(packed.T).view(">u8")                    # [E][ceil(S/64)]
+                keys = [words[:, w] for w in range(words.shape[1] - 1, -1, -1)] + [d_host.sum(axis=0)]
                 self.egene_order = np.lexsort(keys)
                 d_host = np.ascontiguousarray(d_host[:, self.egene_order])
             else:
