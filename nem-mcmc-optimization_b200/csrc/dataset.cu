@@ -22,8 +22,9 @@ namespace {
 // pair-merged table kernel (score_tc.cu): 32 accumulator columns per graph, S + 9 K rows <= 64
 bool pair_supported(int S) { return S >= 33 && S <= 52; }
 // multi-level table kernel (score_tc.cu, EPI_LUTM): same operand image as the pair kernel, S + 9 K rows <= 128 and a
-// compact table of (S+1)(S+2)/2 <= kLutmStride entries per level
-bool lutm_supported(int S) { return S >= 64 && S <= NEMB200_LUTM_MAX_S; }
+// compact table of (S+1)(S+2)/2 <= kLutmStride entries per level.  Meant for 64 <= S <= 118; smaller S use it when the
+// error rates put the single-scale table out of range (e.g. 55 <= S <= 63 at alpha = 0.05, beta = 0.1)
+bool lutm_supported(int S) { return S >= 16 && S <= NEMB200_LUTM_MAX_S; }
 
 struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, lutm, sumN, counters, total; int W, n_mtiles; };
 Layout make_layout(int S, int E) {
@@ -174,7 +175,9 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   // `step` = 121 + T - 1 binary orders higher, and level 0 must hold vmax + log2(S+1) without overflow (T = 90 is
   // the selection threshold of the epilogue: a level is used iff its sum is >= 2^-T)
   h->lutm_levels = 0;
-  h->CS_lutm = (S + 7) / 8 * 8;  // same graphs per tile as h->G: 4 at S = 64, else 2
+  h->CS_lutm = (S + 7) / 8 * 8;
+  h->G_lutm = 256 / h->CS_lutm < 16 ? 256 / h->CS_lutm : 16;  // graphs per tile: a multiple of 4, or 2 (S > 64)
+  h->G_lutm = h->G_lutm >= 4 ? (h->G_lutm & ~3) : 2;
   if (lutm_supported(S)) {
     const double T = 90.0, step = 121.0 + T - 1.0, top = vmax + log2((double)S + 1.0);
     for (int lv = 2; lv <= NEMB200_LUTM_LEVELS && h->lutm_levels == 0; ++lv)

@@ -249,7 +249,7 @@ constexpr int kMinChainsForTwoGroups = 512;
 constexpr int kSmsLeftFree = 20;  // per score launch in two-group mode (measured: 108 vs 126 us/iteration at 1024 chains)
 static int first_group_size(const nemb200_dataset *h, int n) {
   if (n < kMinChainsForTwoGroups || mcmc_fused_preferred(h, n)) return n;
-  const int G = h->lut_valid ? h->G_lut : (h->G > 0 ? h->G : 1);
+  const int G = h->lut_valid ? h->G_lut : (!h->fixed_valid && h->lutm_levels > 0 ? h->G_lutm : (h->G > 0 ? h->G : 1));
   return ((n / 2 + G - 1) / G) * G;  // whole MMA N tiles in the first group
 }
 

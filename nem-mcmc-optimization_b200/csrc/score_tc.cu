@@ -1181,7 +1181,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
     impl = h->lut_valid ? NEMB200_SCORE_TC_LUT
                         : (h->fixed_valid ? NEMB200_SCORE_TC_EX2 : (h->lutm_levels > 0 ? NEMB200_SCORE_TC_LUTM : NEMB200_SCORE_TC_EX2_2PASS));
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUTM || h->lutm_levels > 0,
-               "multi-level table epilogue not available for this dataset (needs 64 <= S <= %d, S=%d)", NEMB200_LUTM_MAX_S, h->S);
+               "multi-level table epilogue not available for this dataset (needs 16 <= S <= %d and a range of at most three levels, S=%d)", NEMB200_LUTM_MAX_S, h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_PAIR || h->pair_ok, "pair-merged table epilogue not available for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUT || h->lut_valid, "exp-table epilogue not valid for this dataset (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_EX2 || h->fixed_valid, "fixed-scale ex2 epilogue not valid for this dataset");
@@ -1195,7 +1195,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   const bool pair = impl == NEMB200_SCORE_TC_PAIR;
   const bool lut = impl == NEMB200_SCORE_TC_LUT;
   const bool lutm = impl == NEMB200_SCORE_TC_LUTM;
-  const int G = pair ? kPairG : (lut ? h->G_lut : h->G);  // graphs per MMA N tile of the kernel that will run
+  const int G = pair ? kPairG : (lut ? h->G_lut : (lutm ? h->G_lutm : h->G));  // graphs per MMA N tile of the kernel that will run
   const int CS = pair ? kPairCS : (lutm ? h->CS_lutm : h->CS);
   const WsLay wl = ws_layout(h, n, pair);
   uint8_t *wb = reinterpret_cast<uint8_t *>(ws);

@@ -157,7 +157,7 @@ def test_score_synthetic_vs_oracle(nb, S, E, n):
     assert np.allclose(ds.score_graphs(graphs, impl="witness"), ref, rtol=REL_WITNESS)
     impls = [i for i in TC_IMPLS if (i != "lut" or ds.lut_valid) and (i != "ex2" or S <= 54)]
     assert impls
-    assert (ds.lutm_levels > 0) == (64 <= S <= 118)
+    assert (ds.lutm_levels > 0) == (16 <= S <= 118)
     if ds.lutm_levels:
         impls.append("lutm")
     for impl in impls:
@@ -199,7 +199,7 @@ def test_score_other_error_rates_and_unsupported(nb):
         ds.score_graphs(np.zeros((1, 100, 100), dtype=np.uint8), impl="lut")   # table epilogue needs S <= 63
 
 
-@pytest.mark.parametrize("S", [64, 100, 118])
+@pytest.mark.parametrize("S", [17, 40, 56, 63, 64, 100, 118])
 def test_score_multilevel_table_extremes(nb, S):
     """Multi-level table epilogue (csrc/score_tc.cu: graph_lse_levels): every E-gene's terms span hundreds of binary
     orders, and which level is used depends on the E-gene.  Extreme data (all ones: the largest possible terms, all
@@ -210,7 +210,7 @@ def test_score_multilevel_table_extremes(nb, S):
     D = (rng.random((S, E)) < 0.5).astype(np.uint8)
     D[:, :64] = 1; D[:, 64:128] = 0
     D[:, 128:192] = (rng.random((S, 64)) < 0.95); D[:, 192:256] = (rng.random((S, 64)) < 0.05)
-    D[:, 256:256 + S] = np.eye(S, dtype=np.uint8)[:, :min(S, E - 256)]
+    D[:, 256:256 + S] = np.eye(S, dtype=np.uint8)
     graphs = np.concatenate([rand_dags(rng, 9, S, p=0.3), rand_dags(rng, 4, S, p=0.02),
                              np.stack([orc.order_to_graph(rng.permutation(S)) for _ in range(3)]).astype(np.uint8),
                              np.zeros((1, S, S), dtype=np.uint8), np.ones((1, S, S), dtype=np.uint8)])
@@ -231,7 +231,7 @@ def test_score_multilevel_table_extremes(nb, S):
         assert np.allclose(ds.score_graphs(graphs), w, rtol=REL_TC)       # auto, whatever it picks
         ref = c_oracle.score_batch(graphs[:3], D, A, B, nthreads=3)
         assert np.allclose(w[:3], ref, rtol=REL_WITNESS)
-    assert {2, 3} <= seen, seen
+    assert {2, 3} <= seen or S < 64, seen
 
 
 @pytest.mark.parametrize("S", [33, 40, 47, 50, 52])
