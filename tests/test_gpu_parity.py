@@ -382,6 +382,33 @@ def test_mcmc_trajectory_vs_oracle(nb, S, E, rule, use_nem, impl):
     assert 0 < res.accept_counts.sum() < n_chains * n_iter
 
 
+@pytest.mark.parametrize("S,E,impl", [(70, 300, "auto"), (100, 260, "lutm"), (100, 260, "ex2_2pass"), (58, 200, "auto")])
+def test_mcmc_trajectory_large_S_vs_oracle(nb, S, E, impl):
+    """The device-resident loop around the S > 54 score paths (multi-level table epilogue = what `auto` picks, and the
+    max-subtracted ex2 epilogue): same accept decisions, orders and edge counts as the oracle chain."""
+    _, _, D = orc.synth_dataset(S, E, seed=S)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rng = np.random.default_rng(S + 1)
+    cand = (rng.random((S, S)) < 0.2).astype(np.uint8)
+    n_chains, n_iter, burn = 5, 120, 20
+    gamma = 2.0 * S / E
+    orders0 = np.stack([rng.permutation(S) for _ in range(n_chains)]).astype(np.int32)
+    ds = nb.Dataset(D, A, B, sort_egenes=True)
+    assert not ds.lut_valid and ds.lutm_levels >= 2
+    st = ds.run_chains(orders0, n_iter, gamma, swap_prob=0.9, seed=5, chain_offset=11, rule=1, cand=cand, use_nem=True,
+                       burn_in=burn, trace=True, impl=impl)
+    res = st.result()
+    total = np.zeros((S, S), dtype=np.int64)
+    for c in range(n_chains):
+        ref = c_oracle.mcmc_chain(D, A, B, orders0[c], n_iter, gamma, swap_prob=0.9, seed=5, chain=11 + c, rule=1,
+                                  cand=cand, use_nem=True, burn_in=burn, keep_scores=True)
+        _compare_chain(res, c, ref, S)
+        assert np.allclose(res.score_trace[:, 0, c], ref["all_score_list"][1:], rtol=1e-6)
+        total += ref["edge_counts"]
+    assert np.array_equal(res.edge_counts, total)
+    assert 0 < res.accept_counts.sum() < n_chains * n_iter
+
+
 def test_mcmc_with_pair_merged_score(nb):
     """The device loop with the pair-merged score kernel (impl="pair") reproduces the oracle chain draw for draw."""
     S, E = 40, 200
