@@ -39,39 +39,88 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_closure(const uint32_t 
 
 // ---- closure, large batches of small graphs (S <= 32): one THREAD per graph -----------------------------
 // The whole S x S bit matrix of a graph lives in 32 registers of one thread, so the Warshall update is two
-// instructions per (i, k) pair with no shuffles; a CTA stages its 128 graphs through shared memory so that
-// global loads/stores stay coalesced (odd row stride: conflict-free).  ~3x fewer warp instructions per graph
-// than the warp-per-graph kernel; used when the batch is large enough to fill the machine (config 5).
+// instructions per (i, k) pair with no shuffles.  A CTA's 128 graphs are one contiguous block of 128*S words:
+// it comes in with ONE bulk (TMA) copy global -> shared on an mbarrier and leaves with one bulk copy shared ->
+// global, so no thread spends instructions or latency on staging (the first version staged with a per-word loop
+// and two integer divisions per word, and was bound by that loop's load latency: 1.27 TB/s at 1 M graphs).
+// Thread t reads its rows at stride S words: conflict-free for odd S, gcd(S,32)-way otherwise, so S with
+// gcd(S,32) > 4 - and blocks the bulk copy cannot take (ragged last CTA, misaligned views) - are staged by
+// the threads into an odd-stride layout instead.
+// Compiled per S (1..32): only S rows and S steps exist, and the update is forced to two instructions per (i, k)
+// pair (bit test into a predicate + predicated OR; the compiler's own choice was a three-instruction mask form
+// over all 32 x 32 pairs).
 constexpr int kThreadClosureBlock = 128;
-__global__ void __launch_bounds__(kThreadClosureBlock) k_closure_thread(const uint32_t *__restrict__ adj, int n, int S,
+template <int S>
+__global__ void __launch_bounds__(kThreadClosureBlock) k_closure_thread(const uint32_t *__restrict__ adj, int n,
                                                                         uint32_t *__restrict__ out) {
-  __shared__ uint32_t sh[kThreadClosureBlock * 33];
+  __shared__ __align__(128) uint32_t sh[kThreadClosureBlock * 33];
+  __shared__ __align__(8) uint64_t bar;
   const int g0 = blockIdx.x * kThreadClosureBlock, ng = min(kThreadClosureBlock, n - g0);
-  const int stride = S | 1;
   const uint32_t *src = adj + (size_t)g0 * S;
-  for (int i = threadIdx.x; i < ng * S; i += kThreadClosureBlock) sh[(i / S) * stride + (i % S)] = src[i];
-  __syncthreads();
+  uint32_t *dst = out + (size_t)g0 * S;
+  const uint32_t bytes = (uint32_t)(ng * S) * 4u;
+  const int g32 = S & -S;  // largest power of two dividing S (S <= 32) = gcd(S, 32)
+  const bool bulk = g32 <= 4 && (bytes & 15u) == 0u && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0u;  // CTA-uniform
+  const int stride = bulk ? S : (S | 1);
+  if (bulk) {
+    const uint32_t bar_a = smem_u32(&bar), sh_a = smem_u32(sh);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sh_a),
+                   "l"(src), "r"(bytes), "r"(bar_a)
+                   : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    uint32_t done;
+    do {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+          "selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(bar_a)
+          : "memory");
+    } while (!done);
+  } else {
+    for (int i = threadIdx.x; i < ng * S; i += kThreadClosureBlock) sh[(i / S) * stride + (i % S)] = src[i];
+    __syncthreads();
+  }
   if ((int)threadIdx.x < ng) {
-    const uint32_t full = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
-    uint32_t r[32];
+    constexpr uint32_t full = S >= 32 ? 0xffffffffu : ((1u << S) - 1u);
+    uint32_t r[S];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = i < S ? (sh[threadIdx.x * stride + i] & full) : 0u;
+    for (int i = 0; i < S; ++i) r[i] = sh[threadIdx.x * stride + i] & full;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      if (k < S) {
-        const uint32_t rk = r[k];
+    for (int k = 0; k < S; ++k) {
+      const uint32_t rk = r[k];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if ((r[i] >> k) & 1u) r[i] |= rk;
+      for (int i = 0; i < S; ++i) {
+        if (i == k) continue;  // row k |= row k changes nothing
+        asm("{\n.reg .pred p;\n.reg .b32 t;\n"
+            "and.b32 t, %0, %2;\n"
+            "setp.ne.u32 p, t, 0;\n"
+            "@p or.b32 %0, %0, %1;\n}"
+            : "+r"(r[i])
+            : "r"(rk), "r"(1u << k));
       }
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < S) sh[threadIdx.x * stride + i] = r[i];
+    for (int i = 0; i < S; ++i) sh[threadIdx.x * stride + i] = r[i];
   }
-  __syncthreads();
-  uint32_t *dst = out + (size_t)g0 * S;
-  for (int i = threadIdx.x; i < ng * S; i += kThreadClosureBlock) dst[i] = sh[(i / S) * stride + (i % S)];
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(sh)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the read
+    }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ng * S; i += kThreadClosureBlock) dst[i] = sh[(i / S) * stride + (i % S)];
+  }
 }
 
 // ---- order -> graph: one warp per chain ----------------------------------------------------------
@@ -165,7 +214,15 @@ int launch_closure(const uint32_t *adj, int n, int S, uint32_t *out, cudaStream_
   if (n == 0) return 0;
   int W = (S + 31) / 32, grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (W == 1 && n >= 8192) {  // enough graphs to fill the machine with one thread per graph
-    k_closure_thread<<<(n + kThreadClosureBlock - 1) / kThreadClosureBlock, kThreadClosureBlock, 0, st>>>(adj, n, S, out);
+    const int tg = (n + kThreadClosureBlock - 1) / kThreadClosureBlock;
+#define NEMB_CT(s_) case s_: k_closure_thread<s_><<<tg, kThreadClosureBlock, 0, st>>>(adj, n, out); break;
+    switch (S) {
+      NEMB_CT(1) NEMB_CT(2) NEMB_CT(3) NEMB_CT(4) NEMB_CT(5) NEMB_CT(6) NEMB_CT(7) NEMB_CT(8) NEMB_CT(9) NEMB_CT(10) NEMB_CT(11)
+      NEMB_CT(12) NEMB_CT(13) NEMB_CT(14) NEMB_CT(15) NEMB_CT(16) NEMB_CT(17) NEMB_CT(18) NEMB_CT(19) NEMB_CT(20) NEMB_CT(21)
+      NEMB_CT(22) NEMB_CT(23) NEMB_CT(24) NEMB_CT(25) NEMB_CT(26) NEMB_CT(27) NEMB_CT(28) NEMB_CT(29) NEMB_CT(30) NEMB_CT(31)
+      NEMB_CT(32)
+    }
+#undef NEMB_CT
     NEMB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
