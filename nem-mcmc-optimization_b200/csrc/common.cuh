@@ -36,6 +36,7 @@ struct nemb200_dataset {
   float *lutm;        // [levels][NEMB200_LUTM_STRIDE] multi-level compact exp table (64 <= S <= 118)
   int CS_lutm;        // accumulator columns per graph of the multi-level table kernel: S rounded up to a multiple of 8
   int G_lutm;         // graphs per MMA N tile of that kernel
+  uint8_t *tile_first;  // [n_mtiles] first (highest-scale) table level E tile m needs (dataset.cu: k_tile_levels)
   int lutm_levels;    // 0 = not usable for this dataset, else 1..3 levels cover the dynamic range
   double lutm_scale[NEMB200_LUTM_LEVELS];  // scale of each level, highest first
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)

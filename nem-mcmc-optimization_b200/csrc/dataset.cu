@@ -26,7 +26,7 @@ bool pair_supported(int S) { return S >= 33 && S <= 52; }
 // error rates put the single-scale table out of range (e.g. 55 <= S <= 63 at alpha = 0.05, beta = 0.1)
 bool lutm_supported(int S) { return S >= 16 && S <= NEMB200_LUTM_MAX_S; }
 
-struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, lutm, sumN, counters, total; int W, n_mtiles; };
+struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, lutm, tile_first, sumN, counters, total; int W, n_mtiles; };
 Layout make_layout(int S, int E) {
   Layout L;
   L.W = (S + 31) / 32;
@@ -38,6 +38,7 @@ Layout make_layout(int S, int E) {
   L.lut = off; off = align_up(off + 64 * 64 * 4, 1024);
   L.tabs = off; off = align_up(off + 65 * 66 / 2 * 4, 1024);
   L.lutm = off; off = align_up(off + (lutm_supported(S) ? (size_t)NEMB200_LUTM_LEVELS * NEMB200_LUTM_STRIDE * 4 : 0), 1024);
+  L.tile_first = off; off = align_up(off + (lutm_supported(S) ? (size_t)L.n_mtiles : 0), 1024);
   L.sumN = off; off = align_up(off + 8, 1024);
   L.counters = off; off = align_up(off + 64 * 4, 1024);
   L.total = off;
@@ -123,6 +124,31 @@ __global__ void k_build_lutm(int S, double alpha2, double beta2, double s0, doub
   }
 }
 
+// Per E tile: the lowest-scale table level that cannot overflow for any of the tile's E-genes, whatever the graph.  A site's
+// term is 2^(alpha2*p + beta2*q) with p <= ones(e), q <= S - ones(e), so x <= max(alpha2,0)*ones(e) + max(beta2,0)*(S-ones(e));
+// levels above tile_first[m] are not needed for tile m (the epilogue skips their look-ups).  With the E-genes stored
+// sorted by their number of ones the tiles are homogeneous and most of them need the last level only.
+__global__ void k_tile_levels(const uint32_t *dcol, int S, int E, int W, int n_mtiles, double alpha2, double beta2, int levels,
+                              double s0, double s1, double s2, uint8_t *tile_first) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_mtiles) return;
+  const double ap = alpha2 > 0 ? alpha2 : 0.0, bp = beta2 > 0 ? beta2 : 0.0;
+  double bound = 0.0;
+  for (int e = m * 128; e < m * 128 + 128 && e < E; ++e) {
+    int ones = 0;
+    for (int w = 0; w < W; ++w) ones += __popc(dcol[(size_t)e * W + w]);
+    bound = fmax(bound, ap * ones + bp * (S - ones));
+  }
+  const double top = bound + log2((double)S + 1.0);
+  int first = 0;
+  for (int l = 1; l < levels; ++l) {
+    const double s = l == 1 ? s1 : s2;
+    if (top < s + 127.0) first = l;
+  }
+  (void)s0;
+  tile_first[m] = (uint8_t)first;
+}
+
 }  // namespace
 
 extern "C" size_t nemb200_dataset_bytes(int S, int E) {
@@ -188,6 +214,10 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   if (h->lutm_levels > 0)
     k_build_lutm<<<(NEMB200_LUTM_STRIDE + 255) / 256, 256, 0, st>>>(S, h->alpha2, h->beta2, h->lutm_scale[0], h->lutm_scale[1],
                                                                   h->lutm_scale[2], h->lutm_levels, h->lutm);
+  h->tile_first = base + L.tile_first;
+  if (h->lutm_levels > 0)
+    k_tile_levels<<<(L.n_mtiles + 127) / 128, 128, 0, st>>>(h->dcol, S, E, L.W, L.n_mtiles, h->alpha2, h->beta2, h->lutm_levels,
+                                                             h->lutm_scale[0], h->lutm_scale[1], h->lutm_scale[2], h->tile_first);
   if (h->pair_ok || h->lutm_levels > 0) k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 1, h->a_pair);
   k_sumN<<<1, 256, 0, st>>>(h->dcol, (size_t)E_pad * L.W, A, h->sumN);
   k_build_lut<<<16, 256, 0, st>>>(S, h->alpha2, h->beta2, (double)h->scale, h->lut, h->tabs);

@@ -85,6 +85,7 @@ struct Params {
   float kc;              // EX2: bias_j = kc * c_j - s
   float scale;           // s
   float lvl_scale[3];    // EPI_LUTM: scale of each table level, highest first
+  const uint8_t *tile_first;  // EPI_LUTM: per E tile, the first level its E-genes can need
   // pair kernel: per graph kPairCS columns of (site, partner or 255); 255,255 = padding column
   const uint8_t *plan;
   const float *tables;   // pair kernel: per graph kPairCap floats (the graph's pair tables, built by the planner)
@@ -327,35 +328,43 @@ __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *
 // largest term from below by 2^0, and the scales (dataset.cu) are spaced so that the FIRST level whose sum reaches
 // 2^-90 has neither overflowed nor lost a term within 2^-22 of the sum; the last level always qualifies (it holds
 // the null term 2^-89).  Returns log2(1 + sum_j 2^x_j).
-template <int NLEV, int N>
+template <int MASK, int N>  // MASK: which levels are looked up (bit l = level l)
 __device__ __forceinline__ void level_add(const uint32_t (&r)[N], float &a0, float &a1, float &a2) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    a0 += lds_f32(r[i]);
-    a1 += lds_f32_off<kLutmStride * 4>(r[i]);
-    if (NLEV > 2) a2 += lds_f32_off<2 * kLutmStride * 4>(r[i]);
+    if (MASK & 1) a0 += lds_f32(r[i]);
+    if (MASK & 2) a1 += lds_f32_off<kLutmStride * 4>(r[i]);
+    if (MASK & 4) a2 += lds_f32_off<2 * kLutmStride * 4>(r[i]);
   }
 }
 // columns [0, n), n a multiple of 8 (padding columns look up an entry that is zero at every level, so nothing in
 // here is predicated: the first version spent more issue slots on ISETP/FSEL than on look-ups).  Keeping the TMEM
 // load of the next chunk in flight during this chunk's look-ups (two register buffers) was measured much slower
 // (2890 vs 1736 us at S=100, E=100k, 512 graphs).
-template <int NLEV>
-__device__ __forceinline__ void level_sums(uint32_t taddr, int n, float &a0, float &a1, float &a2) {
-  a0 = 0.f; a1 = 0.f; a2 = 0.f;
+template <int MASK>
+__device__ __forceinline__ void level_sums_mask(uint32_t taddr, int n, float &a0, float &a1, float &a2) {
   int c = 0;
   for (; c + 16 <= n; c += 16) {
     uint32_t r[16];
     TMEM_LD16(taddr + c, r);
     tmem_wait_ld();
-    level_add<NLEV, 16>(r, a0, a1, a2);
+    level_add<MASK, 16>(r, a0, a1, a2);
   }
   if (c < n) {  // warp-uniform
     uint32_t r[8];
     TMEM_LD8(taddr + c, r);
     tmem_wait_ld();
-    level_add<NLEV, 8>(r, a0, a1, a2);
+    level_add<MASK, 8>(r, a0, a1, a2);
   }
+}
+// `first` (warp-uniform, from the dataset's per-E-tile range analysis): levels above it cannot be needed for this
+// tile and are not looked up - with sorted E-genes most tiles need the last level only (one look-up per site)
+template <int NLEV>
+__device__ __forceinline__ void level_sums(uint32_t taddr, int n, int first, float &a0, float &a1, float &a2) {
+  a0 = 0.f; a1 = 0.f; a2 = 0.f;
+  if (first >= NLEV - 1) level_sums_mask<1 << (NLEV - 1)>(taddr, n, a0, a1, a2);
+  else if (NLEV == 3 && first == 1) level_sums_mask<6>(taddr, n, a0, a1, a2);
+  else level_sums_mask<(1 << NLEV) - 1>(taddr, n, a0, a1, a2);
 }
 template <int NLEV>
 __device__ __forceinline__ float levels_log(float a0, float a1, float a2, const Params &p) {
@@ -368,9 +377,9 @@ __device__ __forceinline__ float levels_log(float a0, float a1, float a2, const 
   return log2_split(a2) + p.lvl_scale[2];
 }
 template <int NLEV>
-__device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int n_cols, const Params &p) {
+__device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int n_cols, int first, const Params &p) {
   float a0, a1, a2;
-  level_sums<NLEV>(taddr, n_cols, a0, a1, a2);
+  level_sums<NLEV>(taddr, n_cols, first, a0, a1, a2);
   return levels_log<NLEV>(a0, a1, a2, p);
 }
 // Two graphs per tile (S > 64) would leave two of the four epilogue warpgroups idle: instead warpgroups 2h and 2h+1
@@ -378,11 +387,11 @@ __device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int n_cols, co
 // the even one through shared memory (slot = tile parity; a 256-thread named barrier per tile).  The accumulator
 // hand-back (t_empty counts all 16 warps) keeps the odd warpgroup from running two tiles ahead, so two slots suffice.
 template <int NLEV>
-__device__ __forceinline__ void tile_epilogue_split(uint32_t taddr_graph, const Params &p, bool valid, int half, int pair,
+__device__ __forceinline__ void tile_epilogue_split(uint32_t taddr_graph, const Params &p, bool valid, int first, int half, int pair,
                                                     float *xch, int tw, double &part0) {
   const int Sh = ((p.CS + 15) >> 4) << 3;  // both halves are multiples of 8 columns
   float a0, a1, a2;
-  level_sums<NLEV>(taddr_graph + (half ? Sh : 0), half ? p.CS - Sh : Sh, a0, a1, a2);
+  level_sums<NLEV>(taddr_graph + (half ? Sh : 0), half ? p.CS - Sh : Sh, first, a0, a1, a2);
   if (half) { xch[tw] = a0; xch[128 + tw] = a1; if (NLEV > 2) xch[256 + tw] = a2; }
   if (pair == 0) asm volatile("bar.sync 8, 256;" ::: "memory"); else asm volatile("bar.sync 9, 256;" ::: "memory");
   if (!half) {
@@ -395,13 +404,13 @@ __device__ __forceinline__ void tile_epilogue_split(uint32_t taddr_graph, const 
 
 template <int EPI, int NLEV>
 __device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const float *sBias, const Params &p, bool valid,
-                                                      int ng_mine, double (&part)[kMaxG / 4]) {
+                                                      int ng_mine, double (&part)[kMaxG / 4], int first = 0) {
   const int S = p.S, bstride = kBiasStride * (S > 64 ? 2 : 1);
 #pragma unroll
   for (int g = 0; g < kMaxG / 4; ++g) {
     if (g < ng_mine) {
       float l;
-      if constexpr (EPI == EPI_LUTM) l = graph_lse_levels<NLEV>(taddr + g * p.CS, p.CS, p);
+      if constexpr (EPI == EPI_LUTM) l = graph_lse_levels<NLEV>(taddr + g * p.CS, p.CS, first, p);
       else l = S >= 16 ? graph_lse2<EPI, 16>(taddr + g * p.CS, S, sBias + g * bstride, p)
                        : graph_lse2<EPI, 8>(taddr + g * p.CS, S, sBias + g * bstride, p);
       if (valid) part[g] += (double)l;
@@ -830,11 +839,12 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
             const uint32_t taddr = tmem_base + buf * 256u + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16);
             const bool valid = (m0 + t) * 128 + quarter * 32 + lane < p.E;
             if constexpr (EPI == EPI_LUTM) {
+              const int first = (int)p.tile_first[m0 + t];
               if (split)
-                tile_epilogue_split<NLUT>(taddr, p, valid, wg & 1, wg >> 1,
+                tile_epilogue_split<NLUT>(taddr, p, valid, first, wg & 1, wg >> 1,
                                           reinterpret_cast<float *>(smem + L::BIAS) + ((buf * 2 + (wg >> 1)) * 3) * 128, tw, part[0]);
               else
-                tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part);
+                tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part, first);
             } else {
               tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part);
             }
@@ -1206,6 +1216,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   Params p;
   p.phi = phi; p.a_img = (pair || lutm) ? h->a_pair : h->a_lut; p.lut = lutm ? h->lutm : h->lut;
   for (int l = 0; l < 3; ++l) p.lvl_scale[l] = (float)h->lutm_scale[l];
+  p.tile_first = h->tile_first;
   p.partials = reinterpret_cast<double *>(wb + wl.partials);
   p.n_graphs = n; p.S = h->S; p.W = h->W; p.E = h->E; p.G = G;
   p.n_mtiles = h->n_mtiles; p.n_slots = kMaxSlots;

@@ -140,7 +140,18 @@ class Dataset:
                     packed = np.concatenate([packed, np.zeros((pad, packed.shape[1]), dtype=np.uint8)])
                 words = np.ascontiguousarray(packed.T).view(">u8")                    # [E][ceil(S/64)]
                 keys = [words[:, w] for w in range(words.shape[1] - 1, -1, -1)] + [d_host.sum(axis=0)]
-                self.egene_order = np.lexsort(keys)
+                order = np.lexsort(keys)
+                # whole tiles of 128 E-genes are then dealt from both ends (lightest, heaviest, second lightest, ...):
+                # tiles stay homogeneous, but every contiguous run of tiles - what one CTA of the score kernel gets -
+                # has the same mix of cheap and expensive tiles (the multi-level table epilogue skips table levels
+                # that a tile's E-genes cannot need); the ragged last tile stays last
+                nfull = len(order) // 128
+                if nfull > 2:
+                    deal = np.empty(nfull, dtype=np.int64)
+                    deal[0::2] = np.arange((nfull + 1) // 2)
+                    deal[1::2] = nfull - 1 - np.arange(nfull // 2)
+                    order = np.concatenate([order[:nfull * 128].reshape(nfull, 128)[deal].ravel(), order[nfull * 128:]])
+                self.egene_order = order
                 d_host = np.ascontiguousarray(d_host[:, self.egene_order])
             else:
                 self.egene_order = np.arange(d_host.shape[1])

@@ -220,6 +220,11 @@ def test_score_multilevel_table_extremes(nb, S):
         ds = nb.Dataset(D, A, B)
         w = ds.score_graphs(graphs, impl="witness")
         seen.add(ds.lutm_levels)
+        if ds.lutm_levels:
+            # E-genes stored sorted: homogeneous tiles, most of which skip the upper table levels (k_tile_levels)
+            ds_sorted = nb.Dataset(D, A, B, sort_egenes=True)
+            got_s = ds_sorted.score_graphs(graphs, impl="lutm")
+            assert np.allclose(got_s, w, rtol=REL_TC), (alpha, beta, np.abs(got_s / w - 1).max())
         if ds.lutm_levels == 0:
             with pytest.raises(nb._lib.NemB200Error):
                 ds.score_graphs(graphs, impl="lutm")
