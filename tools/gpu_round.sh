@@ -12,4 +12,8 @@ python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/plain_a.log 2>&1 && 
 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/plain_b.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:k_score_tc -s 6 -c 1 -o gpurun_out/prof_score \
       python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/ncu_b.log 2>&1
+python tools/kernel_time.py 100 100000 128 lutm > gpurun_out/plain_c.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:k_score_tc -s 3 -c 1 -o gpurun_out/prof_lutm \
+      python tools/kernel_time.py 100 100000 128 lutm > gpurun_out/ncu_c.log 2>&1
+python tools/closure_time.py > gpurun_out/closure_time.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -1; cat gpurun_out/bench.json | cut -c1-1500; cat gpurun_out/bench_reference.json | cut -c1-600; tail -2 gpurun_out/bench.err

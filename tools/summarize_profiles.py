@@ -21,9 +21,11 @@ with open(os.path.join(out, f"{tag}_launches.md"), "w") as f:
 import shutil
 shutil.copy(os.path.join(go, "launches.csv"), os.path.join(out, f"{tag}_launches.csv"))
 
-raw = subprocess.run(["ncu", "-i", os.path.join(go, "prof_score.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h = rr[0]; units = rr[1]; vals = rr[2]
+def raw_page(rep):
+    raw = subprocess.run(["ncu", "-i", os.path.join(go, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    return rr[0], rr[1], rr[2]
+h, units, vals = raw_page("prof_score.ncu-rep")
 want = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
@@ -51,5 +53,19 @@ try:
     print("dram bytes per launch", total)
 except Exception as ex:
     print("traffic.json not written:", ex)
+# second capture: the multi-level table kernel at the config-4 shape (tools/kernel_time.py 100 100000 128 lutm)
+if os.path.exists(os.path.join(go, "prof_lutm.ncu-rep")):
+    h2, u2, v2 = raw_page("prof_lutm.ncu-rep")
+    name2 = v2[h2.index("Kernel Name")] if "Kernel Name" in h2 else "k_score_tc"
+    with open(os.path.join(out, f"{tag}_lutm_ncu.md"), "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none` of the multi-level table score kernel\n\nkernel: `{name2}`  "
+                "(one launch = 128 graphs, S=100, E=100000, E-genes sorted: `python tools/kernel_time.py 100 100000 128 lutm`)\n\n"
+                "| metric | value | unit |\n|---|---:|---|\n")
+        for w in want + ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+                         "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active"]:
+            if w in h2:
+                i = h2.index(w)
+                f.write(f"| {w} | {v2[i]} | {u2[i]} |\n")
+    print(open(os.path.join(out, f"{tag}_lutm_ncu.md")).read())
 print(open(os.path.join(out, f"{tag}_launches.md")).read())
 print(open(os.path.join(out, f"{tag}_score_kernel_ncu.md")).read())
