@@ -69,6 +69,14 @@ int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int n);
 int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_t *d_out_bits,
                         void *stream);
 
+/* ---- transitive reduction: replaces utils.transitive_reduction (utils.py:120-129) as used by
+ *      main.output_handling (main.py:50) on the best graph of a run, for a batch of graphs (e.g. the best graph of
+ *      every chain).  Reproduces the reference's in-place update order exactly: for a closed DAG the result is its
+ *      Hasse diagram; graphs with cycles or self loops get what the reference's triple loop leaves.  In-place
+ *      allowed (d_out == d_adj). */
+int nemb200_transitive_reduction_u32(const uint32_t *d_adj_bits, int n_graphs, int S,
+                                     uint32_t *d_out_bits, void *stream);
+
 /* ---- batched NEM score: replaces compute_ll_ratios + calculate_ll for binary graphs
  *      (nem.py:72-86 driven as nem.py:132-142; utils.py:66-94; nem_order_mcmc.py:79-93 without
  *      the expit quirk).  d_phi_bits: n_graphs closed (or not) graphs; score is

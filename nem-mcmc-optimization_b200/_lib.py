@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
     L.nemb200_dataset_destroy.argtypes = [vp]
     L.nemb200_dataset_info.argtypes = [vp, C.POINTER(i64), i32]
     L.nemb200_closure_u32.argtypes = [vp, i32, i32, vp, vp]
+    L.nemb200_transitive_reduction_u32.argtypes = [vp, i32, i32, vp, vp]
     L.nemb200_score_workspace_bytes.restype = sz
     L.nemb200_score_workspace_bytes.argtypes = [vp, i32]
     L.nemb200_score_workspace_bytes_impl.restype = sz
@@ -79,7 +80,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ["nemb200_version", "nemb200_last_error", "nemb200_dataset_bytes", "nemb200_dataset_create",
-           "nemb200_dataset_destroy", "nemb200_dataset_info", "nemb200_closure_u32",
+           "nemb200_dataset_destroy", "nemb200_dataset_info", "nemb200_closure_u32", "nemb200_transitive_reduction_u32",
            "nemb200_score_workspace_bytes", "nemb200_score_workspace_bytes_impl", "nemb200_score_batch", "nemb200_order_to_graph",
            "nemb200_mcmc_workspace_bytes", "nemb200_mcmc_run", "nemb200_replica_exchange",
            "nemb200_edge_counts_reduce", "nemb200_cell_ratios", "nemb200_cell_ll_workspace_bytes",

@@ -73,6 +73,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 // internal launchers (defined in the per-kernel .cu files)
 int launch_closure(const uint32_t *adj, int n, int S, uint32_t *out, cudaStream_t st);
+int launch_transitive_reduction(const uint32_t *adj, int n, int S, uint32_t *out, cudaStream_t st);
 int launch_order_to_graph(const int32_t *orders, int n, int S, int rule, const uint32_t *cand, int use_nem,
                           uint32_t *out, cudaStream_t st);
 size_t score_witness_workspace_bytes(int n);

@@ -292,6 +292,13 @@ extern "C" int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int
   return launch_closure(d_adj_bits, n_graphs, S, d_out_bits, (cudaStream_t)stream);
 }
 
+extern "C" int nemb200_transitive_reduction_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_t *d_out_bits,
+                                                void *stream) {
+  NEMB_REQUIRE(S >= 1 && S <= NEMB200_MAX_S, "S must be in [1,%d] (got %d)", NEMB200_MAX_S, S);
+  NEMB_REQUIRE(n_graphs >= 0 && (n_graphs == 0 || (d_adj_bits && d_out_bits)), "bad arguments");
+  return launch_transitive_reduction(d_adj_bits, n_graphs, S, d_out_bits, (cudaStream_t)stream);
+}
+
 extern "C" int nemb200_order_to_graph(const int32_t *d_orders, int n_chains, int S, int rule, const uint32_t *d_cand_bits,
                                       int use_nem, uint32_t *d_out_bits, void *stream) {
   NEMB_REQUIRE(S >= 1 && S <= NEMB200_MAX_S, "S must be in [1,%d] (got %d)", NEMB200_MAX_S, S);

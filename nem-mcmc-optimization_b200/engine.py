@@ -100,6 +100,21 @@ def closure(graphs, S: int | None = None, device=None, return_bits: bool = False
     return unpack_adj(out.cpu().numpy().view(np.uint32), S)
 
 
+def transitive_reduction(graphs, S: int | None = None, device=None, return_bits: bool = False):
+    """Transitive reduction of a batch of graphs on the GPU with the reference's exact in-place semantics
+    (utils.transitive_reduction, utils.py:120-129): e.g. the best graph of every chain of a run."""
+    device = _require_cuda(device)
+    if S is None:
+        S = np.asarray(graphs).shape[-2]
+    bits = _bits_to_device(graphs, S, device)
+    out = torch.empty_like(bits)
+    st = torch.cuda.current_stream(device)
+    _lib.check(_lib.lib().nemb200_transitive_reduction_u32(_ptr(bits), bits.shape[0], S, _ptr(out), _stream_ptr(st)))
+    if return_bits:
+        return out
+    return unpack_adj(out.cpu().numpy().view(np.uint32), S)
+
+
 @dataclass
 class ChainResult:
     best_scores: np.ndarray      # (n,)

@@ -119,16 +119,55 @@ def read_csv_to_adj(pathname):
 
 
 def transitive_reduction(adj_matrix):
-    """utils.py:120-129 (host; result post-processing)."""
-    a = np.array(adj_matrix, copy=True)
-    n = a.shape[0]
-    for k in range(n):
-        via = np.outer(a[:, k] != 0, a[k, :] != 0)
-        np.fill_diagonal(via, False)
-        a[via] = 0
-    return a
+    """utils.py:120-129 (result post-processing), on the GPU (`nemb200_transitive_reduction_u32`): the
+    reference's in-place triple loop, reproduced exactly - the Hasse diagram for a closed DAG; nonzero entries count
+    as edges and the result is 0/1 in the input's dtype."""
+    a = np.asarray(adj_matrix)
+    out = engine.transitive_reduction((a != 0).astype(np.uint8)[None], S=a.shape[0])[0]
+    return out.astype(a.dtype if a.dtype != bool else np.uint8)
 
 
 def hamming_distance(mat_a, mat_b):
     """utils.py:148-149."""
     return np.sum(np.abs(np.asarray(mat_a) - np.asarray(mat_b)))
+
+
+
+# ---- result post-processing (SURVEY 8 f-4) ----------------------------------------------------------------
+def dot_string(adj_matrix):
+    """The DOT text DAGs/dot.py:28-36 builds for an adjacency matrix: one ``i -> j;`` line per nonzero entry."""
+    a = np.asarray(adj_matrix)
+    lines = ["digraph {"]
+    for i in range(len(a)):
+        for j in range(len(a)):
+            if a[i][j] != 0:
+                lines.append("    {} -> {};".format(i, j))
+    return "\n".join(lines) + "\n}"
+
+
+def generate_dot_from_matrix(adj_matrix, output_file):
+    """DAGs/dot.py:28-42 without its ``os.chdir('../')`` side effect: writes the DOT file where it is told to."""
+    with open(output_file, "w") as f:
+        f.write(dot_string(adj_matrix))
+    return output_file
+
+
+def output_handling(best_dag, output_dir, true_adj=None):
+    """main.output_handling (main.py:44-55) without the graphviz rendering: closes the best graph (utils.ancestor,
+    :46), reduces it (utils.transitive_reduction, :50), writes ``infer_closed.dot`` and ``infer_red.dot`` into
+    `output_dir`, and - when the true network is given - reports the Hamming distance main.py:106 prints, between the closures and between their Hasse diagrams.
+    -> dict(closed, reduced, paths, hamming_closed, hamming_reduced)."""
+    os.makedirs(output_dir, exist_ok=True)
+    best = (np.asarray(best_dag) != 0).astype(int)
+    closed = ancestor(best)
+    reduced = transitive_reduction(best)
+    paths = [generate_dot_from_matrix(closed, os.path.join(output_dir, "infer_closed.dot")),
+             generate_dot_from_matrix(reduced, os.path.join(output_dir, "infer_red.dot"))]
+    res = {"closed": closed, "reduced": reduced, "paths": paths, "hamming_closed": None, "hamming_reduced": None}
+    if true_adj is not None:
+        truth = (np.asarray(true_adj) != 0).astype(int)
+        truth_closed = ancestor(truth)
+        res["hamming_closed"] = int(hamming_distance(closed, truth_closed))
+        # canonical forms on both sides: the Hasse diagrams of the two closures
+        res["hamming_reduced"] = int(hamming_distance(transitive_reduction(closed), transitive_reduction(truth_closed)))
+    return res

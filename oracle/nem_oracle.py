@@ -129,16 +129,43 @@ def closure_bool(adj):
 
 
 def transitive_reduction(adj):
-    """utils.py:120-129."""
+    """utils.py:120-129, statement for statement: the matrix is updated IN PLACE while k, i, j run, and
+    adj[i][k] is re-read for every j - which matters only when node k carries a self loop (then row i loses
+    its entries j <= k of row k and stops, and row k itself collapses to the self loop)."""
     a = np.array(adj, copy=True)
     n = a.shape[0]
     for k in range(n):
         for i in range(n):
-            if a[i][k]:
-                for j in range(n):
-                    if i != j and a[k][j]:
-                        a[i][j] = 0
+            for j in range(n):
+                if i != j and a[i][k] and a[k][j]:
+                    a[i][j] = 0
     return a
+
+
+def transitive_reduction_rows(adj):
+    """The same result computed row-wise per step k (the form the CUDA kernel uses on bit rows): with rk = row k at
+    the start of step k and self = rk[k]:  rows i < k holding k lose rk's entries (only those j <= k if self),
+    never their own diagonal; row k collapses to its self loop if self; rows i > k holding k lose rk's entries if
+    not self, else only their entry k."""
+    a = np.array(adj, copy=True) != 0
+    n = a.shape[0]
+    for k in range(n):
+        rk = a[k].copy()
+        self_loop = bool(rk[k])
+        low = np.arange(n) <= k
+        for i in range(n):
+            if not a[i][k]:
+                continue
+            if i == k:
+                a[k] = False
+                a[k][k] = True
+            elif self_loop and i > k:
+                a[i][k] = False
+            else:
+                m = rk & low if self_loop else rk.copy()
+                m[i] = False
+                a[i] &= ~m
+    return a.astype(np.asarray(adj).dtype)
 
 
 # --------------------------------------------------------------------------

@@ -765,3 +765,46 @@ def test_score_stream_pipelined_host_batches(nb):
     for k in range(5):
         assert np.array_equal(out[k].numpy(), ds.score_graphs(batches[k], close=True)), k
     ds.score_stream([], out)  # empty sequence is a no-op
+
+
+# ------------------------------------------------------------------------------------------ f-4: post-processing
+def test_transitive_reduction_golden_and_oracle(nb):
+    """nemb200_transitive_reduction_u32 vs the reference's own outputs (tests/golden/reduction.npz: closed DAGs,
+    unclosed DAGs, cyclic digraphs, digraphs with self loops, S = 1..70) and vs the oracle on larger batches."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reduction.npz"))
+    for c in range(int(z["n_cases"])):
+        a = z[f"in{c}"]
+        got = nb.transitive_reduction(a[None])[0]
+        assert np.array_equal(got, z[f"red{c}"]), (c, a.shape)
+        assert np.array_equal(nb.utils.transitive_reduction(a.astype(int)), z[f"red{c}"].astype(int))
+    rng = np.random.default_rng(8)
+    for S in (7, 32, 50, 97, 128):
+        graphs = np.concatenate([rand_dags(rng, 20, S, p=0.2), rand_dags(rng, 10, S, p=0.1, closed=False),
+                                 (rng.random((10, S, S)) < 0.05).astype(np.uint8), np.ones((1, S, S), dtype=np.uint8)])
+        got = nb.transitive_reduction(graphs)
+        for g in range(len(graphs)):
+            assert np.array_equal(got[g], orc.transitive_reduction_rows(graphs[g])), (S, g)
+        # closed DAG: the reduction is the Hasse diagram - closing it again gives the graph back, and it is minimal
+        closed = graphs[:20]
+        red = got[:20]
+        assert np.array_equal(nb.closure(red), closed)
+        assert (red <= closed).all()
+    # in place, on device bit rows
+    bits = torch.from_numpy(nb.pack_adj(graphs).view(np.int32)).cuda()
+    out = nb.transitive_reduction(bits, S=128, return_bits=True)
+    assert np.array_equal(nb.unpack_adj(out.cpu().numpy().view(np.uint32), 128), got)
+
+
+def test_output_handling_writes_dot_files(nb, golden, tmp_path):
+    """main.output_handling (main.py:44-55) minus graphviz: closed + reduced DOT files of the best graph."""
+    arr, meta = golden
+    adj, red = arr["adj11"], arr["red11"]   # the network's closed form and its reduced form (networks/network11*.csv)
+    res = nb.utils.output_handling(red, str(tmp_path / "output"), true_adj=adj)
+    assert np.array_equal(res["closed"], arr["anc_red11"])       # utils.ancestor(reduced), produced by the reference
+    assert np.array_equal(res["reduced"], orc.transitive_reduction_rows((np.asarray(red) != 0).astype(int)))
+    for pth, mat in zip(res["paths"], (res["closed"], res["reduced"])):
+        text = open(pth).read()
+        assert text.startswith("digraph {") and text.endswith("}")
+        assert text.count("->") == int(np.count_nonzero(mat))
+    assert res["hamming_closed"] == 0 and res["hamming_reduced"] == 0

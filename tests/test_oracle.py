@@ -199,3 +199,18 @@ def test_fit_minimiser_against_bruteforce():
         G = -np.log1p(c[None, :] * grid[:, None]).sum(1) + np.abs(grid - anc) + grid * (1 - grid)
         Gs = -np.sum(np.log1p(c * s)) + abs(s - anc) + s * (1 - s)
         assert Gs <= G.min() + 1e-9, (trial, s, grid[G.argmin()])
+
+
+def test_transitive_reduction_golden():
+    """utils.transitive_reduction / hamming_distance of the reference on 60 graphs (closed DAGs, unclosed DAGs, cyclic
+    digraphs, digraphs with self loops; S = 1..70) - tests/golden/make_golden_reduction.py.  Both oracle forms (the
+    statement-for-statement triple loop and the per-row form the CUDA kernel uses) must reproduce them."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reduction.npz"))
+    n = int(z["n_cases"])
+    assert n == 60
+    for c in range(n):
+        a, want = z[f"in{c}"].astype(np.int64), z[f"red{c}"].astype(np.int64)
+        assert np.array_equal(orc.transitive_reduction_rows(a), want), c
+        if a.shape[0] <= 33:   # the triple loop is O(S^3) Python
+            assert np.array_equal(orc.transitive_reduction(a), want), c
+        assert int(np.sum(np.abs(a - z[f"other{c}"].astype(np.int64)))) == int(z[f"ham{c}"])
