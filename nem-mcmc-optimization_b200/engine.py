@@ -85,6 +85,31 @@ def _bits_to_device(graphs, S, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(bits).view(np.int32)).to(device, non_blocking=False)
 
 
+def egene_storage_order(d_host: np.ndarray) -> np.ndarray:
+    """Storage order of the E-genes (columns of the 0/1 matrix D) for `Dataset(sort_egenes=True)`; host logic.
+    The score is a sum over E-genes, so their order is free.  They are sorted by number of ones (it bounds every
+    count p, so the 32 E-genes of a warp hit neighbouring table entries: conflict-free look-ups), then by the pattern
+    itself (row 0 most significant; compared as big-endian 64-bit words: S/64 sort keys instead of S).  Whole tiles
+    of 128 E-genes are then dealt from both ends (lightest, heaviest, second lightest, ...): tiles stay homogeneous -
+    the multi-level table epilogue skips table levels a tile's E-genes cannot need - while every contiguous run of
+    tiles, which is what one CTA of the score kernel gets, has the same mix of cheap and expensive tiles.  The
+    ragged last tile stays last."""
+    packed = np.packbits(d_host, axis=0)                                  # row 0 = MSB of byte 0
+    pad = (-packed.shape[0]) % 8
+    if pad:
+        packed = np.concatenate([packed, np.zeros((pad, packed.shape[1]), dtype=np.uint8)])
+    words = np.ascontiguousarray(packed.T).view(">u8")                    # [E][ceil(S/64)]
+    keys = [words[:, w] for w in range(words.shape[1] - 1, -1, -1)] + [d_host.sum(axis=0)]
+    order = np.lexsort(keys)
+    nfull = len(order) // 128
+    if nfull > 2:
+        deal = np.empty(nfull, dtype=np.int64)
+        deal[0::2] = np.arange((nfull + 1) // 2)
+        deal[1::2] = nfull - 1 - np.arange(nfull // 2)
+        order = np.concatenate([order[:nfull * 128].reshape(nfull, 128)[deal].ravel(), order[nfull * 128:]])
+    return order
+
+
 def closure(graphs, S: int | None = None, device=None, return_bits: bool = False):
     """Transitive closure of a batch of graphs on the GPU (replaces utils.ancestor, utils.py:37-54)."""
     device = _require_cuda(device)
@@ -147,26 +172,7 @@ class Dataset:
                 D = D.detach().cpu().numpy()
             d_host = np.ascontiguousarray((np.asarray(D) != 0).astype(np.uint8))
             if sort_egenes and d_host.shape[1] > 1:
-                # number of ones first (it bounds every count p), then the pattern itself (row 0 most significant);
-                # the pattern is compared as big-endian 64-bit words: S/64 sort keys instead of S
-                packed = np.packbits(d_host, axis=0)                                  # row 0 = MSB of byte 0
-                pad = (-packed.shape[0]) % 8
-                if pad:
-                    packed = np.concatenate([packed, np.zeros((pad, packed.shape[1]), dtype=np.uint8)])
-                words = np.ascontiguousarray(packed.T).view(">u8")                    # [E][ceil(S/64)]
-                keys = [words[:, w] for w in range(words.shape[1] - 1, -1, -1)] + [d_host.sum(axis=0)]
-                order = np.lexsort(keys)
-                # whole tiles of 128 E-genes are then dealt from both ends (lightest, heaviest, second lightest, ...):
-                # tiles stay homogeneous, but every contiguous run of tiles - what one CTA of the score kernel gets -
-                # has the same mix of cheap and expensive tiles (the multi-level table epilogue skips table levels
-                # that a tile's E-genes cannot need); the ragged last tile stays last
-                nfull = len(order) // 128
-                if nfull > 2:
-                    deal = np.empty(nfull, dtype=np.int64)
-                    deal[0::2] = np.arange((nfull + 1) // 2)
-                    deal[1::2] = nfull - 1 - np.arange(nfull // 2)
-                    order = np.concatenate([order[:nfull * 128].reshape(nfull, 128)[deal].ravel(), order[nfull * 128:]])
-                self.egene_order = order
+                self.egene_order = egene_storage_order(d_host)
                 d_host = np.ascontiguousarray(d_host[:, self.egene_order])
             else:
                 self.egene_order = np.arange(d_host.shape[1])

@@ -70,6 +70,27 @@ def test_host_utils_match_reference_semantics(golden):
     assert utils.hamming_distance(np.eye(3), np.zeros((3, 3))) == 3
 
 
+def test_egene_storage_order_is_a_tile_homogeneous_permutation():
+    """Dataset(sort_egenes=True): a permutation; every 128-E-gene tile holds a contiguous range of the sort by number
+    of ones (homogeneous tiles), tiles alternate light / heavy, the ragged tail stays last."""
+    rng = np.random.default_rng(0)
+    for S, E in [(5, 100), (50, 1000), (100, 3000), (70, 128 * 7), (64, 129)]:
+        d = (rng.random((S, E)) < rng.random(E)[None, :]).astype(np.uint8)
+        order = engine.egene_storage_order(d)
+        assert sorted(order.tolist()) == list(range(E))
+        ones = d.sum(axis=0)[order]
+        nfull = E // 128
+        tiles = ones[:nfull * 128].reshape(nfull, 128) if nfull else np.zeros((0, 128))
+        assert all((np.diff(t) >= 0).all() for t in tiles)                       # sorted inside a tile
+        if nfull > 2:
+            lo, hi = tiles.min(axis=1), tiles.max(axis=1)
+            ranked = np.argsort(lo, kind="stable")
+            assert all(hi[ranked[i]] <= lo[ranked[i + 1]] for i in range(nfull - 1))   # tiles do not overlap
+            assert lo[0] == ones.min() and hi[1] == ones[:nfull * 128].max()    # lightest first, heaviest second
+        if E % 128 and nfull:
+            assert ones[nfull * 128:].min() >= tiles.max()                       # the ragged tail is the heaviest
+
+
 def test_dot_text_matches_reference_format():
     """DAGs/dot.py:28-36: 'digraph {', one '    i -> j;' line per nonzero entry in row-major order, '}'."""
     a = np.array([[0, 1, 1], [0, 0, 2], [0, 0, 0]])
