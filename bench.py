@@ -441,7 +441,13 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "traffic": traffic, "kernel": "k_score_tc (tcgen05 kind::i8 + fused logsumexp)",
                          "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": flops,
-                         "exps_per_launch": float((S + 1) * E * CHAINS), "peak_source": how},
+                         "exps_per_launch": float((S + 1) * E * CHAINS), "peak_source": how,
+                         # what actually limits the kernel: one shared-memory look-up per (site, E-gene),
+                         # i.e. S * E_pad / 32 LDS wavefronts per graph, against 1 wavefront/clk/SM (the LSU data pipe;
+                         # tools/micro_pipes.cu reaches 0.88 with 16 warps of pure look-ups)
+                         "co_limit": {"unit": "LDS wavefronts/clk/SM", "peak": 1.0, "measured_ceiling_16_warps": 0.88,
+                                      "achieved": (S * ((E + 127) // 128 * 128) / 32.0 * CHAINS)
+                                                  / (ms_kernel * 1e-3 * (sampler.summary().get("sm_mhz") or 1965.0) * 1e6 * 148)}},
             "e2e": {"value": CHAINS * world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch_bytes,
                     "d2h_bytes_per_step": CHAINS * 8, "api": "Dataset.score_stream: closure + score_batch on pinned host bit rows, scores copied back, copies double-buffered against the kernels"},
             "gpu_launches": 3 * K,
