@@ -450,7 +450,9 @@ def run_gpu(args, rank, world, local_rank):
                                                   / (ms_kernel * 1e-3 * (sampler.summary().get("sm_mhz") or 1965.0) * 1e6 * 148)}},
             "e2e": {"value": CHAINS * world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch_bytes,
                     "d2h_bytes_per_step": CHAINS * 8, "api": "Dataset.score_stream: closure + score_batch on pinned host bit rows, scores copied back, copies double-buffered against the kernels"},
-            "gpu_launches": 3 * K,
+            # timed region of `value`: per step k_closure + k_score_tc (its finalize is fused into the last CTA for
+            # batches <= 2048 graphs, else a separate k_finalize launch)
+            "gpu_launches": (2 if CHAINS <= 2048 else 3) * K,
             "mcmc": {"value": state.n * world * mc_iters / (ms_mcmc * 1e-3), "unit": "chain-iterations/s", "iters": mc_iters,
                      "chains": state.n * world, "ms_per_iter": ms_mcmc / mc_iters, "accept_rate": acc_rate,
                      "rule": "masked+closure", "collectives": "edge-count all-reduce + best-graph broadcast, once per run",
