@@ -39,7 +39,7 @@ enum {
   NEMB200_SCORE_TC_EX2_2PASS = 4, /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
   NEMB200_MCMC_FUSED = 5, /* nemb200_mcmc_run only: persistent one-CTA-per-chain kernel (small S*E) */
   NEMB200_SCORE_TC_PAIR = 6, /* tcgen05 GEMM + pair-merged table epilogue: two attachment sites per look-up (33 <= S <= 52) */
-  NEMB200_SCORE_TC_LUTM = 7  /* tcgen05 GEMM + multi-level exp-table epilogue: dynamic ranges of up to ~630 binary orders, 16 <= S <= 118 */
+  NEMB200_SCORE_TC_LUTM = 7  /* tcgen05 GEMM + multi-level exp-table epilogue: dynamic ranges of up to ~630 binary orders, 16 <= S <= 125 */
 };
 
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */

@@ -8,11 +8,11 @@
 
 #define NEMB200_LOG2E 1.4426950408889634074
 #define NEMB200_LN2 0.69314718055994530942
-// multi-level table epilogue (score_tc.cu, EPI_LUTM): floats per level (n(n+1)/2 + p, n <= 118), number of levels
-#define NEMB200_LUTM_STRIDE 7168
+// multi-level table epilogue (score_tc.cu, EPI_LUTM): floats per level (n(n+1)/2 + p, n <= 125), number of levels
+#define NEMB200_LUTM_STRIDE 8192
 #define NEMB200_LUTM_LEVELS 3
-#define NEMB200_LUTM_MAX_S 118
-#define NEMB200_LUTM_ZERO 7160   // entry that is 0 at every level (n = 119 > S): what padding columns look up
+#define NEMB200_LUTM_MAX_S 125   // S + 3 K rows <= 128; (S+1)(S+2)/2 <= 8001 table entries per level
+#define NEMB200_LUTM_ZERO 8190   // entry that is 0 at every level (n = 127 > S): what padding columns look up
 
 // ---- host handle ---------------------------------------------------------------------------
 struct nemb200_dataset {
@@ -31,9 +31,10 @@ struct nemb200_dataset {
   uint32_t *dcol;     // [E_pad][W]  bit i of row e = D[i][e]
   uint8_t *a_lut;     // [n_mtiles][KA][128 x 128 B] bf16 operand image, values {4,256}+bias row
   uint8_t *a_pair;    // operand image of the pair-merged kernel: 4*D, eight constant rows of 128 and one of 4
+  uint8_t *a_lutm;    // operand image of the multi-level table kernel: 4*D, two constant rows of 128 and one of 4
   int pair_ok;        // pair-merged table kernel usable (table valid, 33 <= S <= 52)
   float *tabs;        // compact exp table of the pair planner: tabs[n(n+1)/2 + p] = lut[n-p][p], n <= S
-  float *lutm;        // [levels][NEMB200_LUTM_STRIDE] multi-level compact exp table (64 <= S <= 118)
+  float *lutm;        // [levels][NEMB200_LUTM_STRIDE] multi-level compact exp table (16 <= S <= 125)
   int CS_lutm;        // accumulator columns per graph of the multi-level table kernel: S rounded up to a multiple of 8
   int G_lutm;         // graphs per MMA N tile of that kernel
   uint8_t *tile_first;  // [n_mtiles] first (highest-scale) table level E tile m needs (dataset.cu: k_tile_levels)

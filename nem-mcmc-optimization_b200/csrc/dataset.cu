@@ -21,12 +21,12 @@ namespace {
 
 // pair-merged table kernel (score_tc.cu): 32 accumulator columns per graph, S + 9 K rows <= 64
 bool pair_supported(int S) { return S >= 33 && S <= 52; }
-// multi-level table kernel (score_tc.cu, EPI_LUTM): same operand image as the pair kernel, S + 9 K rows <= 128 and a
-// compact table of (S+1)(S+2)/2 <= kLutmStride entries per level.  Meant for 64 <= S <= 118; smaller S use it when the
+// multi-level table kernel (score_tc.cu, EPI_LUTM): its own operand image (4*D + three constant rows, S + 3 K rows <= 128)
+// and a compact table of (S+1)(S+2)/2 <= kLutmStride entries per level.  Meant for 64 <= S <= 125; smaller S use it when the
 // error rates put the single-scale table out of range (e.g. 55 <= S <= 63 at alpha = 0.05, beta = 0.1)
 bool lutm_supported(int S) { return S >= 16 && S <= NEMB200_LUTM_MAX_S; }
 
-struct Layout { size_t dcol, a_lut, a_pair, lut, tabs, lutm, tile_first, sumN, counters, total; int W, n_mtiles; };
+struct Layout { size_t dcol, a_lut, a_pair, a_lutm, lut, tabs, lutm, tile_first, sumN, counters, total; int W, n_mtiles; };
 Layout make_layout(int S, int E) {
   Layout L;
   L.W = (S + 31) / 32;
@@ -34,7 +34,8 @@ Layout make_layout(int S, int E) {
   size_t off = 0;
   L.dcol = off; off = align_up(off + (size_t)L.n_mtiles * 128 * L.W * 4, 1024);
   L.a_lut = off; off = align_up(off + (size_t)L.n_mtiles * 128 * 128, 1024);
-  L.a_pair = off; off = align_up(off + ((pair_supported(S) || lutm_supported(S)) ? (size_t)L.n_mtiles * 128 * 128 : 0), 1024);
+  L.a_pair = off; off = align_up(off + (pair_supported(S) ? (size_t)L.n_mtiles * 128 * 128 : 0), 1024);
+  L.a_lutm = off; off = align_up(off + (lutm_supported(S) ? (size_t)L.n_mtiles * 128 * 128 : 0), 1024);
   L.lut = off; off = align_up(off + 64 * 64 * 4, 1024);
   L.tabs = off; off = align_up(off + 65 * 66 / 2 * 4, 1024);
   L.lutm = off; off = align_up(off + (lutm_supported(S) ? (size_t)NEMB200_LUTM_LEVELS * NEMB200_LUTM_STRIDE * 4 : 0), 1024);
@@ -59,8 +60,9 @@ __global__ void k_pack_dcol(const uint8_t *D, int S, int E, int W, int E_pad, ui
 
 // u8 A-operand image, one 16 KB SWIZZLE_128B atom per 128 E-genes:
 //   a[e][k] = 2 if D[k][e] else 128 (k < S, e < E); a[e][S] = 128 for every row (exp-table base row); 0 elsewhere
-// pair != 0: the image of the pair-merged kernel: a[e][k] = 4*D[k][e]; a[e][S..S+7] = 128, a[e][S+8] = 4 for every row
+// pair == 1: the image of the pair-merged kernel: a[e][k] = 4*D[k][e]; a[e][S..S+7] = 128, a[e][S+8] = 4 for every row
 // (constant rows: the B operand's entries there add the byte address of the column's table)
+// pair == 2: the image of the multi-level table kernel: the same with two rows of 128 (S, S+1) and the 4 in row S+2
 __global__ void k_build_aimg(const uint32_t *dcol, int S, int E, int W, int E_pad, int pair, uint8_t *img) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (row e, 16-byte chunk c)
   if (idx >= E_pad * 8) return;
@@ -71,8 +73,8 @@ __global__ void k_build_aimg(const uint32_t *dcol, int S, int E, int W, int E_pa
     uint32_t v = 0;
     if (pair) {
       if (k < S) v = (e < E && ((dcol[(size_t)e * W + (k >> 5)] >> (k & 31)) & 1u)) ? 4u : 0u;
-      else if (k < S + 8) v = 128u;
-      else if (k == S + 8) v = 4u;
+      else if (k < S + (pair == 2 ? 2 : 8)) v = 128u;
+      else if (k == S + (pair == 2 ? 2 : 8)) v = 4u;
     } else if (k < S && e < E) v = ((dcol[(size_t)e * W + (k >> 5)] >> (k & 31)) & 1u) ? 2u : 128u;
     else if (k == S) v = 128u;
     bytes[b >> 2] |= v << ((b & 3) * 8);
@@ -173,7 +175,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   h->CS = S;  // set below once the epilogue kind is known
   h->A = A; h->B = B;
   h->alpha2 = -A * NEMB200_LOG2E; h->beta2 = B * NEMB200_LOG2E;
-  h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_pair = base + L.a_pair;
+  h->dcol = (uint32_t *)(base + L.dcol); h->a_lut = base + L.a_lut; h->a_pair = base + L.a_pair; h->a_lutm = base + L.a_lutm;
   h->lut = (float *)(base + L.lut); h->tabs = (float *)(base + L.tabs); h->sumN = (double *)(base + L.sumN);
   h->counters = (int *)(base + L.counters);
   // single-scale validity: largest log2-domain value over the lattice p+q<=S
@@ -196,7 +198,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
   k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 0, h->a_lut);
   h->pair_ok = h->lut_valid && pair_supported(S);
-  // multi-level table epilogue (64 <= S <= 118): the null site bounds every E-gene's largest term from below by
+  // multi-level table epilogue (16 <= S <= 125): the null site bounds every E-gene's largest term from below by
   // 2^0, so the levels only have to cover [0, vmax]: the lowest level has scale T-1, each further one sits
   // `step` = 121 + T - 1 binary orders higher, and level 0 must hold vmax + log2(S+1) without overflow (T = 90 is
   // the selection threshold of the epilogue: a level is used iff its sum is >= 2^-T)
@@ -218,7 +220,8 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   if (h->lutm_levels > 0)
     k_tile_levels<<<(L.n_mtiles + 127) / 128, 128, 0, st>>>(h->dcol, S, E, L.W, L.n_mtiles, h->alpha2, h->beta2, h->lutm_levels,
                                                              h->lutm_scale[0], h->lutm_scale[1], h->lutm_scale[2], h->tile_first);
-  if (h->pair_ok || h->lutm_levels > 0) k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 1, h->a_pair);
+  if (h->pair_ok) k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 1, h->a_pair);
+  if (h->lutm_levels > 0) k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 2, h->a_lutm);
   k_sumN<<<1, 256, 0, st>>>(h->dcol, (size_t)E_pad * L.W, A, h->sumN);
   k_build_lut<<<16, 256, 0, st>>>(S, h->alpha2, h->beta2, (double)h->scale, h->lut, h->tabs);
   cudaError_t e = cudaGetLastError();

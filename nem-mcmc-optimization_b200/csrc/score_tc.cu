@@ -55,7 +55,7 @@ constexpr int kPairCap = 1568;              // table entries per graph (planner 
 constexpr int kPairLim = 256;               // table entries per pair (keeps every B weight <= 128)
 constexpr int kPairZero = 2040;             // float index (in the single-site table region) of a permanent 0
 constexpr int kPlanColBytes = 80;           // planner output per accumulator column: 64 B-operand bytes + 16 bytes of meta
-constexpr int kLutmStride = NEMB200_LUTM_STRIDE;  // floats per level of the multi-level table (n(n+1)/2 + p, n <= 118)
+constexpr int kLutmStride = NEMB200_LUTM_STRIDE;  // floats per level of the multi-level table (n(n+1)/2 + p, n <= 125)
 template <bool PAIR, bool LUT3 = false>
 struct Lay {
   static constexpr int STAGES = (PAIR || LUT3) ? 3 : 4;
@@ -320,7 +320,7 @@ __device__ __forceinline__ float graph_lse2(uint32_t taddr, int S, const float *
   return log2_split(ex2f(-p.scale) + acc0 + acc1) + p.scale;
 }
 
-// ---- multi-level table epilogue (EPI_LUTM, 64 <= S <= 118, NLEV = 2 or 3 levels): a site's term is
+// ---- multi-level table epilogue (EPI_LUTM, 16 <= S <= 125, NLEV = 2 or 3 levels): a site's term is
 // V(n_j, p) = 2^(x - s_l) with n_j = |ancestors-or-self of j| known per column and p the count of ones among them, so
 // the accumulator is made the shared-memory address of entry n_j(n_j+1)/2 + p of the level-0 table; the same entry at
 // the lower scales sits kLutmStride floats further each.  One site costs NLEV look-ups and no exponential.  A single
@@ -657,12 +657,14 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
         *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
       }
       if constexpr (EPI == EPI_LUTM) {
-        // constant K rows (A operand: 128 in row S, 4 in row S+8): the byte address of the column's first table entry,
-        // V(n_j, 0) of level 0; padding columns and absent graphs look up an entry that is zero at every level
+        // constant K rows (A operand: 128 in rows S and S+1, 4 in row S+2): the byte address of the column's first
+        // table entry, V(n_j, 0) of level 0; padding columns and absent graphs look up an entry that is zero at every level
         const uint32_t addr = sbase + L::LUT + 4u * (uint32_t)(used ? cnt * (cnt + 1) / 2 : NEMB200_LUTM_ZERO);
-        if ((addr >> 7) > 255u) asm volatile("trap;");  // level 0 must sit in the first 32 KB of shared memory
-        brow[sw128((uint32_t)col, (uint32_t)S)] = (uint8_t)(addr >> 7);
-        brow[sw128((uint32_t)col, (uint32_t)(S + 8))] = (uint8_t)((addr & 127u) >> 2);
+        const uint32_t q = addr >> 7, b0 = q < 255u ? q : 255u;
+        if (q - b0 > 255u) asm volatile("trap;");  // level 0 must sit in the first 64 KB of shared memory
+        brow[sw128((uint32_t)col, (uint32_t)S)] = (uint8_t)b0;
+        brow[sw128((uint32_t)col, (uint32_t)(S + 1))] = (uint8_t)(q - b0);
+        brow[sw128((uint32_t)col, (uint32_t)(S + 2))] = (uint8_t)((addr & 127u) >> 2);
       } else {
         if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
       }
@@ -1214,7 +1216,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
                "batch too large for one launch (%d graphs x %d E tiles): split it", n, h->n_mtiles);
   const unsigned T = (unsigned)n_ntiles * (unsigned)h->n_mtiles;
   Params p;
-  p.phi = phi; p.a_img = (pair || lutm) ? h->a_pair : h->a_lut; p.lut = lutm ? h->lutm : h->lut;
+  p.phi = phi; p.a_img = pair ? h->a_pair : (lutm ? h->a_lutm : h->a_lut); p.lut = lutm ? h->lutm : h->lut;
   for (int l = 0; l < 3; ++l) p.lvl_scale[l] = (float)h->lutm_scale[l];
   p.tile_first = h->tile_first;
   p.partials = reinterpret_cast<double *>(wb + wl.partials);
@@ -1222,7 +1224,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   p.n_mtiles = h->n_mtiles; p.n_slots = kMaxSlots;
   p.CS = CS;
   p.nmma = (G * CS + 15) / 16 * 16;
-  p.ksteps = (pair || lutm) ? (h->S + 9 + 31) / 32 : (h->S + (lut ? 1 : 0) + 31) / 32;
+  p.ksteps = pair ? (h->S + 9 + 31) / 32 : (lutm ? (h->S + 3 + 31) / 32 : (h->S + (lut ? 1 : 0) + 31) / 32);
   // accumulator a = 4p + 256q = 256c - 252p  ->  x = alpha2*p + beta2*q = k1*a + kc*c
   const double kappa2 = h->alpha2 - h->beta2;
   p.k1 = (float)(-kappa2 / 252.0);

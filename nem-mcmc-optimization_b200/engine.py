@@ -197,7 +197,7 @@ class Dataset:
         _lib.check(L.nemb200_dataset_info(self._h, info, 9))
         self.W, self.graphs_per_tile, self.lut_valid, self.scale_log2, self.n_mtiles = (
             int(info[2]), int(info[4]), bool(info[5]), int(info[6]), int(info[7]))
-        self.lutm_levels = int(info[8])  # levels of the multi-level exp table (64 <= S <= 118), 0 = not usable
+        self.lutm_levels = int(info[8])  # levels of the multi-level exp table (16 <= S <= 125), 0 = not usable
         self._score_ws = None
 
     def __del__(self):

@@ -144,7 +144,7 @@ def test_score_noise_free_small_score(nb, golden):
 
 @pytest.mark.parametrize("S,E,n", [(8, 40, 7), (10, 100, 33), (16, 257, 17), (20, 1000, 64), (30, 5000, 41),
                                    (50, 1000, 23), (50, 10000, 12), (63, 700, 9), (64, 300, 9), (77, 900, 11),
-                                   (100, 1500, 7), (118, 640, 6), (119, 200, 4), (128, 260, 5)])
+                                   (100, 1500, 7), (118, 640, 6), (119, 200, 4), (125, 333, 5), (126, 200, 3), (128, 260, 5)])
 def test_score_synthetic_vs_oracle(nb, S, E, n):
     rng = np.random.default_rng(S * 1000 + E)
     _, _, D = orc.synth_dataset(S, E, seed=S + E)
@@ -157,7 +157,7 @@ def test_score_synthetic_vs_oracle(nb, S, E, n):
     assert np.allclose(ds.score_graphs(graphs, impl="witness"), ref, rtol=REL_WITNESS)
     impls = [i for i in TC_IMPLS if (i != "lut" or ds.lut_valid) and (i != "ex2" or S <= 54)]
     assert impls
-    assert (ds.lutm_levels > 0) == (16 <= S <= 118)
+    assert (ds.lutm_levels > 0) == (16 <= S <= 125)
     if ds.lutm_levels:
         impls.append("lutm")
     for impl in impls:
@@ -199,7 +199,7 @@ def test_score_other_error_rates_and_unsupported(nb):
         ds.score_graphs(np.zeros((1, 100, 100), dtype=np.uint8), impl="lut")   # table epilogue needs S <= 63
 
 
-@pytest.mark.parametrize("S", [17, 40, 56, 63, 64, 100, 118])
+@pytest.mark.parametrize("S", [17, 40, 56, 63, 64, 100, 118, 125])
 def test_score_multilevel_table_extremes(nb, S):
     """Multi-level table epilogue (csrc/score_tc.cu: graph_lse_levels): every E-gene's terms span hundreds of binary
     orders, and which level is used depends on the E-gene.  Extreme data (all ones: the largest possible terms, all
