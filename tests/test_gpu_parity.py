@@ -602,6 +602,18 @@ def test_c_abi_error_paths(nb):
     assert rc < 0 and b"S must be" in L.nemb200_last_error()
     rc = L.nemb200_order_to_graph(C.c_void_p(bits.data_ptr()), 1, S, 1, None, 1, C.c_void_p(bits.data_ptr()), st)
     assert rc < 0 and b"candidate" in L.nemb200_last_error()
+    rc = L.nemb200_transitive_reduction_u32(C.c_void_p(bits.data_ptr()), 1, 0, C.c_void_p(bits.data_ptr()), st)
+    assert rc < 0 and b"S must be" in L.nemb200_last_error()
+    rc = L.nemb200_transitive_reduction_u32(None, 1, S, C.c_void_p(bits.data_ptr()), st)
+    assert rc < 0 and b"bad arguments" in L.nemb200_last_error()
+    assert L.nemb200_transitive_reduction_u32(None, 0, S, None, st) == 0                     # empty batch: nothing to do
+    rc = L.nemb200_score_batch(ds._h, C.c_void_p(bits.data_ptr()), 1, C.c_void_p(out.data_ptr()), C.c_void_p(ds._score_workspace(1)[0].data_ptr()),
+                               ds._score_workspace(1)[1], nb.engine.SCORE_IMPLS["ex2_2pass"], st)
+    assert rc == 0
+    big = nb.Dataset(np.zeros((126, 10), dtype=np.uint8), *orc.nem_constants(0.05, 0.1))       # S > 125: no multi-level table
+    assert big.lutm_levels == 0
+    with pytest.raises(nb._lib.NemB200Error, match="multi-level"):
+        big.score_graphs(np.zeros((1, 126, 126), dtype=np.uint8), impl="lutm")
     with pytest.raises(nb._lib.NemB200Error):
         ds.score_graphs(np.zeros((1, S, S), dtype=np.uint8), impl=17)
     with pytest.raises(ValueError):
