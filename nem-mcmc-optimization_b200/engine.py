@@ -216,16 +216,27 @@ class Dataset:
             self._score_ws = torch.empty(max(need, 1), dtype=torch.uint8, device=self.device)
         return self._score_ws, need
 
+    def max_graphs_per_launch(self) -> int:
+        """Largest batch one score launch takes: the kernel's flat tile index is 32-bit (tiles x CTAs < 4e9; the
+        library refuses larger launches), so very large batches at large E are split here."""
+        per_tile = 2                                   # fewest graphs per MMA N tile of any score kernel
+        n_tiles = int(3.0e9 // (self.n_mtiles * 160))  # 160 > the SM count
+        return max(per_tile * n_tiles // 1024 * 1024, 1024)
+
     def score_bits(self, bits: torch.Tensor, impl="auto", out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
         """Score bit-packed graphs already on the device; returns a float64 CUDA tensor (no sync)."""
         n = int(bits.shape[0])
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=self.device)
-        ws, need = self._score_workspace(n, impl)
         st = stream or torch.cuda.current_stream(self.device)
-        _lib.check(_lib.lib().nemb200_score_batch(self._h, _ptr(bits), n, _ptr(out), _ptr(ws), ws.numel(),
-                                                  SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl),
-                                                  _stream_ptr(st)))
+        code = SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl)
+        step = self.max_graphs_per_launch()
+        ws, need = self._score_workspace(min(n, step), impl)
+        for lo in range(0, max(n, 1), step):           # one launch unless the batch exceeds the launch limit
+            m = min(step, n - lo)
+            _lib.check(_lib.lib().nemb200_score_batch(self._h, _ptr(bits[lo:lo + m]) if n else _ptr(bits), m,
+                                                      _ptr(out[lo:lo + m]) if n else _ptr(out), _ptr(ws), ws.numel(), code,
+                                                      _stream_ptr(st)))
         return out
 
     def score_graphs(self, graphs, impl="auto", close: bool = False) -> np.ndarray:

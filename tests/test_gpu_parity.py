@@ -622,6 +622,23 @@ def test_c_abi_error_paths(nb):
         ds.run_chains(np.zeros((2, S), dtype=np.int32), 1, 0.1)   # not permutations
 
 
+def test_score_batch_split_over_launch_limit(nb):
+    """Batches beyond one launch's 32-bit tile index are split by Dataset.score_bits: same scores as one launch."""
+    S, E, n = 20, 300, 3000
+    rng = np.random.default_rng(5)
+    _, _, D = orc.synth_dataset(S, E, seed=5)
+    ds = nb.Dataset(D, *orc.nem_constants(0.05, 0.1))
+    bits = ds.order_graphs(np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32))
+    whole = ds.score_bits(bits).cpu().numpy()
+    assert ds.max_graphs_per_launch() >= 1 << 20          # E = 300: the limit is far away
+    ds.max_graphs_per_launch = lambda: 1024               # force three launches (1024 + 1024 + 952)
+    assert np.array_equal(ds.score_bits(bits).cpu().numpy(), whole)
+    assert np.allclose(ds.score_bits(bits, impl="witness").cpu().numpy(), whole, rtol=REL_TC)
+    big = nb.Dataset(np.zeros((100, 2_000_000), dtype=np.uint8)[:, :1], *orc.nem_constants(0.05, 0.1))
+    big.n_mtiles = 15626                                   # as for E = 2 000 000: about 2400 graphs per launch
+    assert 1024 <= big.max_graphs_per_launch() <= 4096 and big.max_graphs_per_launch() % 1024 == 0
+
+
 def test_sorted_egenes_and_multichain_loop_path(nb):
     """Dataset(sort_egenes=True) is score-invariant; > 296 chains take the CUDA-graph loop even for a small
     problem and agree with the persistent kernel chain by chain (same global chain ids)."""
