@@ -14,7 +14,8 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+// threads per CTA (template parameter THREADS): 256 for E <= 256, else 512 with two E-genes per thread and pass
+// (S=20 x E=1000 x 64 chains: 3.57 -> 3.2 us per iteration; 1024 threads bring nothing more there)
 // E-genes per thread and pass (template parameter EPT): 4 amortises the site record over four E-genes; with
 // E <= 256 one E-gene per thread keeps four times as many threads busy (S=10 x E=100: 2.42 -> 2.09 us/iteration)
 
@@ -56,7 +57,7 @@ __device__ __forceinline__ float log2_split(float x) {
   return (float)e + l;
 }
 
-template <int TW, int EPT>
+template <int TW, int EPT, int kThreads>
 __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   float *sLut = reinterpret_cast<float *>(smem);                        // 16 KB
@@ -65,9 +66,9 @@ __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
   uint32_t *sCurr = sRows + 64 * 2;                                     // [S][TW] current graph rows
   int *sOrder = reinterpret_cast<int *>(sCurr + 64 * 2);                // [S] current order
   int *sProp = sOrder + 64;                                             // [S] proposed order
-  double *sRed = reinterpret_cast<double *>(sProp + 64);                // [8]
-  int *sFlag = reinterpret_cast<int *>(sRed + 8);                       // accept flag / swap positions
-  uint32_t *sD = reinterpret_cast<uint32_t *>(smem + 16384 + 1024 + 512 + 512 + 256 + 256 + 64 + 64);
+  double *sRed = reinterpret_cast<double *>(sProp + 64);                // [16]: one partial sum per warp
+  int *sFlag = reinterpret_cast<int *>(sRed + 16);                      // accept flag / swap positions
+  uint32_t *sD = reinterpret_cast<uint32_t *>(smem + 16384 + 1024 + 512 + 512 + 256 + 256 + 128 + 64);
 
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.S, E = p.E;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
   }
 }
 
-constexpr int kFixedSmem = 16384 + 1024 + 512 + 512 + 256 + 256 + 64 + 64;
+constexpr int kFixedSmem = 16384 + 1024 + 512 + 512 + 256 + 256 + 128 + 64;
 
 }  // namespace
 
@@ -279,14 +280,14 @@ int launch_mcmc_fused(const nemb200_dataset *h, int n, int64_t n_iters, int64_t 
   const size_t dbytes = (size_t)h->E * h->W * 4;
   p.dcol_in_smem = dbytes <= 96 * 1024;
   const size_t smem = kFixedSmem + (p.dcol_in_smem ? dbytes : 0);
-  const bool one = h->E <= kThreads;  // one E-gene per thread when a single pass covers them all
-#define NEMB_FUSED(TW_, EPT_)                                                                                             \
-  do {                                                                                                                    \
-    NEMB_CHECK_CUDA(cudaFuncSetAttribute(k_mcmc_fused<TW_, EPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_mcmc_fused<TW_, EPT_><<<n, kThreads, smem, st>>>(p);                                                                \
+  const bool one = h->E <= 256;  // one E-gene per thread when a single pass of 256 threads covers them all
+#define NEMB_FUSED(TW_, EPT_, THR_)                                                                                            \
+  do {                                                                                                                         \
+    NEMB_CHECK_CUDA(cudaFuncSetAttribute(k_mcmc_fused<TW_, EPT_, THR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_mcmc_fused<TW_, EPT_, THR_><<<n, THR_, smem, st>>>(p);                                                                   \
   } while (0)
-  if (h->W == 1) { if (one) NEMB_FUSED(1, 1); else NEMB_FUSED(1, 4); }
-  else { if (one) NEMB_FUSED(2, 1); else NEMB_FUSED(2, 4); }
+  if (h->W == 1) { if (one) NEMB_FUSED(1, 1, 256); else NEMB_FUSED(1, 2, 512); }
+  else { if (one) NEMB_FUSED(2, 1, 256); else NEMB_FUSED(2, 2, 512); }
 #undef NEMB_FUSED
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
