@@ -14,8 +14,8 @@
 
 namespace {
 
-// threads per CTA (template parameter THREADS): 256 for E <= 256, else 512 with two E-genes per thread and pass
-// (S=20 x E=1000 x 64 chains: 3.57 -> 3.2 us per iteration; 1024 threads bring nothing more there)
+// threads per CTA (template parameter): two proposer warps + 192 / 256 scorer threads with one E-gene each for
+// E <= 192 / 256, else + 512 scorer threads with two E-genes per thread and pass (1024 E-genes per pass: config 2 in one)
 // E-genes per thread and pass (template parameter EPT): 4 amortises the site record over four E-genes; with
 // E <= 256 one E-gene per thread keeps four times as many threads busy (S=10 x E=100: 2.42 -> 2.09 us/iteration)
 
@@ -57,18 +57,82 @@ __device__ __forceinline__ float log2_split(float x) {
   return (float)e + l;
 }
 
+// One proposal slot: what a proposer warp prepares and the scorer warps consume.
+constexpr int kSlotBytes = 64 * 16 + 64 * 2 * 4 + 64 * 4;  // site records, graph rows, proposed order
+constexpr int kFixedSmem = 16384 + 3 * kSlotBytes + 512 + 256 + 256 + 64;
+
+// Proposal of iteration t (or, with is_init, the unswapped start order) built by ONE warp into a slot: Philox draw ->
+// swapped order (get_new_order :231-255) -> graph rows (:54-77, 210-221, closure utils.py:37-54) -> per attachment site
+// the ancestor mask (column j of I|Phi) and the byte address of its exp-table row.
+template <int TW>
+__device__ __forceinline__ void build_proposal(const FusedParams &p, int c, long long t, bool is_init, const int *base_order,
+                                               uint4 *sSite, uint32_t *sRows, int *sProp, int *sU, uint32_t lutbase) {
+  const int lane = threadIdx.x & 31, S = p.S;
+  uint32_t ctr[4] = {(uint32_t)t, (uint32_t)((unsigned long long)t >> 32), p.chain_offset + (uint32_t)c, 0u};
+  int si = -1, sj = -1;
+  if (!is_init) {
+    philox4x32_10(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    if ((unsigned long long)ctr[0] < p.swap_prob_u33) {
+      si = (int)__umulhi(ctr[1], (uint32_t)S);
+      sj = (int)__umulhi(ctr[2], (uint32_t)(S - 1));
+      if (sj >= si) ++sj;
+    } else {
+      si = (int)__umulhi(ctr[1], (uint32_t)(S - 1));
+      sj = si + 1;
+    }
+  }
+  int labels[TW];
+#pragma unroll
+  for (int tt = 0; tt < TW; ++tt) {
+    const int pos = tt * 32 + lane;
+    const int src = pos == si ? sj : (pos == sj ? si : pos);
+    labels[tt] = pos < S ? base_order[src] : -1;
+  }
+#pragma unroll
+  for (int tt = 0; tt < TW; ++tt)
+    if (tt * 32 + lane < S) sProp[tt * 32 + lane] = labels[tt];
+  uint32_t r[TW][TW];
+  warp_graph_from_labels<TW>(labels, S, p.rule, p.cand, p.use_nem, sRows, r);
+  __syncwarp();
+#pragma unroll
+  for (int tt = 0; tt < TW; ++tt) {
+    const int row = tt * 32 + lane;
+    if (row < S) {
+#pragma unroll
+      for (int w = 0; w < TW; ++w) sRows[row * TW + w] = r[tt][w];
+    }
+  }
+  if (lane == 0) *sU = (int)ctr[3];  // accept uniform word (unused for the start order)
+  __syncwarp();
+  for (int j = lane; j < S; j += 32) {
+    uint32_t m[2] = {0u, 0u};
+    int cnt = 0;
+    for (int a = 0; a < S; ++a) {
+      const uint32_t bit = ((sRows[a * TW + (j >> 5)] >> (j & 31)) & 1u) | (a == j ? 1u : 0u);
+      m[a >> 5] |= bit << (a & 31);
+      cnt += (int)bit;
+    }
+    sSite[j] = make_uint4(m[0], m[1], lutbase + 4u * 64u * (uint32_t)cnt, 0u);
+  }
+}
+
+// Warps 0 and 1 are proposers, the others score.  While the scorers work on the proposal of iteration t, warp 0
+// prepares the proposal of iteration t+1 for the case that t is accepted (base order = the proposal being scored)
+// and warp 1 for the case that it is rejected (base = the current order): the Philox draw does not depend on the
+// state, so after the accept decision the right slot is simply selected and no iteration ever waits for a proposal.
 template <int TW, int EPT, int kThreads>
 __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  float *sLut = reinterpret_cast<float *>(smem);                        // 16 KB
-  uint4 *sSite = reinterpret_cast<uint4 *>(smem + 16384);               // [S]: anc0, anc1, 4*(64*cnt), unused
-  uint32_t *sRows = reinterpret_cast<uint32_t *>(smem + 16384 + 64 * 16);  // [S][TW] proposed graph rows
-  uint32_t *sCurr = sRows + 64 * 2;                                     // [S][TW] current graph rows
-  int *sOrder = reinterpret_cast<int *>(sCurr + 64 * 2);                // [S] current order
-  int *sProp = sOrder + 64;                                             // [S] proposed order
-  double *sRed = reinterpret_cast<double *>(sProp + 64);                // [16]: one partial sum per warp
-  int *sFlag = reinterpret_cast<int *>(sRed + 16);                      // accept flag / swap positions
-  uint32_t *sD = reinterpret_cast<uint32_t *>(smem + 16384 + 1024 + 512 + 512 + 256 + 256 + 128 + 64);
+  float *sLut = reinterpret_cast<float *>(smem);                                   // 16 KB
+  uint8_t *slots = smem + 16384;                                                   // 3 proposal slots
+  uint32_t *sCurr = reinterpret_cast<uint32_t *>(slots + 3 * kSlotBytes);          // [S][TW] current graph rows
+  int *sOrder = reinterpret_cast<int *>(sCurr + 64 * 2);                           // [S] current order
+  double *sRed = reinterpret_cast<double *>(sOrder + 64);                          // [32]: one partial sum per warp
+  int *sFlag = reinterpret_cast<int *>(sRed + 32);                                 // [0] accept flag, [4+s] uniform of slot s
+  uint32_t *sD = reinterpret_cast<uint32_t *>(smem + kFixedSmem);
+  auto slot_site = [&](int s) { return reinterpret_cast<uint4 *>(slots + s * kSlotBytes); };
+  auto slot_rows = [&](int s) { return reinterpret_cast<uint32_t *>(slots + s * kSlotBytes + 64 * 16); };
+  auto slot_prop = [&](int s) { return reinterpret_cast<int *>(slots + s * kSlotBytes + 64 * 16 + 64 * 2 * 4); };
 
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.S, E = p.E;
@@ -87,106 +151,69 @@ __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
   long long n_acc = 0, since = p.iter0;
   uint32_t *counts = p.edge_counts ? p.edge_counts + (size_t)c * S * S : nullptr;
 
-  for (long long it = p.resume ? 0 : -1; it < p.n_iters; ++it) {
+  const long long it0 = p.resume ? 0 : -1;  // -1: score the start order first (method(), :258)
+  int x = 0, sa = 1, sr = 2;                // slot being scored, slots of the two speculative successors
+  if (it0 < p.n_iters && warp == 0)
+    build_proposal<TW>(p, c, p.iter0 + (it0 < 0 ? 0 : it0), it0 < 0, sOrder, slot_site(x), slot_rows(x), slot_prop(x), sFlag + 4 + x, lutbase);
+  __syncthreads();
+  for (long long it = it0; it < p.n_iters; ++it) {
     const bool init = it < 0;
     const long long t = p.iter0 + (init ? 0 : it);
-    uint32_t ctr[4] = {(uint32_t)t, (uint32_t)((unsigned long long)t >> 32), p.chain_offset + (uint32_t)c, 0u};
-    // ---- propose + order -> graph + closure (warp 0) --------------------------------------------------
-    if (warp == 0) {
-      int si = -1, sj = -1;
-      if (!init) {
-        philox4x32_10(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        if ((unsigned long long)ctr[0] < p.swap_prob_u33) {
-          si = (int)__umulhi(ctr[1], (uint32_t)S);
-          sj = (int)__umulhi(ctr[2], (uint32_t)(S - 1));
-          if (sj >= si) ++sj;
-        } else {
-          si = (int)__umulhi(ctr[1], (uint32_t)(S - 1));
-          sj = si + 1;
+    const uint4 *sSite = slot_site(x);
+    if (warp < 2) {
+      // ---- proposers: the two possible proposals of iteration it + 1 -------------------------------------
+      if (it + 1 < p.n_iters) {
+        const int s = warp == 0 ? sa : sr;
+        build_proposal<TW>(p, c, p.iter0 + it + 1, false, warp == 0 ? slot_prop(x) : sOrder, slot_site(s), slot_rows(s), slot_prop(s),
+                           sFlag + 4 + s, lutbase);
+      }
+    } else {
+      // ---- scorers: every thread takes EPT E-genes per pass ----------------------------------------------
+      double sum = 0.0;
+      for (int e0 = (tid - 64) * EPT; e0 < E; e0 += (kThreads - 64) * EPT) {
+        uint32_t d[EPT][TW];
+        float acc[EPT][4];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+#pragma unroll
+          for (int w = 0; w < TW; ++w) d[u][w] = e0 + u < E ? dsrc[(size_t)(e0 + u) * TW + w] : 0u;
+          acc[u][0] = null_term; acc[u][1] = 0.f; acc[u][2] = 0.f; acc[u][3] = 0.f;
         }
-      }
-      int labels[TW];
+        for (int j0 = 0; j0 < S; j0 += 4) {
 #pragma unroll
-      for (int tt = 0; tt < TW; ++tt) {
-        int pos = tt * 32 + lane;
-        int src = pos == si ? sj : (pos == sj ? si : pos);
-        labels[tt] = pos < S ? sOrder[src] : -1;
-      }
-      __syncwarp();
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            if (j < S) {
+              const uint4 site = sSite[j];
 #pragma unroll
-      for (int tt = 0; tt < TW; ++tt)
-        if (tt * 32 + lane < S) sProp[tt * 32 + lane] = labels[tt];
-      uint32_t r[TW][TW];
-      warp_graph_from_labels<TW>(labels, S, p.rule, p.cand, p.use_nem, sRows, r);
-      __syncwarp();
-#pragma unroll
-      for (int tt = 0; tt < TW; ++tt) {
-        int row = tt * 32 + lane;
-        if (row < S) {
-#pragma unroll
-          for (int w = 0; w < TW; ++w) sRows[row * TW + w] = r[tt][w];
-        }
-      }
-      if (lane == 0) sFlag[1] = (int)ctr[3];  // accept uniform word (valid when !init)
-    }
-    __syncthreads();
-    // ---- ancestor masks per attachment site (column j of I|Phi) ------------------------------------------
-    for (int j = tid; j < S; j += kThreads) {
-      uint32_t m[2] = {0u, 0u};
-      int cnt = 0;
-      for (int a = 0; a < S; ++a) {
-        uint32_t bit = ((sRows[a * TW + (j >> 5)] >> (j & 31)) & 1u) | (a == j ? 1u : 0u);
-        m[a >> 5] |= bit << (a & 31);
-        cnt += (int)bit;
-      }
-      sSite[j] = make_uint4(m[0], m[1], lutbase + 4u * 64u * (uint32_t)cnt, 0u);
-    }
-    __syncthreads();
-    // ---- score: every thread takes EPT E-genes per pass -------------------------------------------------
-    double sum = 0.0;
-    for (int e0 = tid * EPT; e0 < E; e0 += kThreads * EPT) {
-      uint32_t d[EPT][TW];
-      float acc[EPT][4];
-#pragma unroll
-      for (int u = 0; u < EPT; ++u) {
-#pragma unroll
-        for (int w = 0; w < TW; ++w) d[u][w] = e0 + u < E ? dsrc[(size_t)(e0 + u) * TW + w] : 0u;
-        acc[u][0] = null_term; acc[u][1] = 0.f; acc[u][2] = 0.f; acc[u][3] = 0.f;
-      }
-      for (int j0 = 0; j0 < S; j0 += 4) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = j0 + jj;
-          if (j < S) {
-            const uint4 site = sSite[j];
-#pragma unroll
-            for (int u = 0; u < EPT; ++u) {
-              int pc = __popc(site.x & d[u][0]);
-              if (TW > 1) pc += __popc(site.y & d[u][1]);
-              // entry [q][p] with q = cnt - p: byte offset 4*(64*cnt - 63*p)
-              acc[u][jj] += lds_f32(site.z - 252u * (uint32_t)pc);
+              for (int u = 0; u < EPT; ++u) {
+                int pc = __popc(site.x & d[u][0]);
+                if (TW > 1) pc += __popc(site.y & d[u][1]);
+                // entry [q][p] with q = cnt - p: byte offset 4*(64*cnt - 63*p)
+                acc[u][jj] += lds_f32(site.z - 252u * (uint32_t)pc);
+              }
             }
           }
         }
+#pragma unroll
+        for (int u = 0; u < EPT; ++u)
+          if (e0 + u < E) sum += (double)(log2_split((acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3])) + p.scale);
       }
 #pragma unroll
-      for (int u = 0; u < EPT; ++u)
-        if (e0 + u < E) sum += (double)(log2_split((acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3])) + p.scale);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) sRed[warp] = sum;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) sRed[warp] = sum;
     __syncthreads();
     // ---- accept (thread 0 decides, everyone applies) ------------------------------------------------------
     if (tid == 0) {
       double v = 0.0;
-      for (int w8 = 0; w8 < kThreads / 32; ++w8) v += sRed[w8];
+      for (int w8 = 2; w8 < kThreads / 32; ++w8) v += sRed[w8];
       const double ll = sumN + NEMB200_LN2 * v;
       bool acc_ok, better;
       if (init) {
         acc_ok = true; better = true;
       } else {
-        const double u = ((double)(uint32_t)sFlag[1] + 0.5) * (1.0 / 4294967296.0);
+        const double u = ((double)(uint32_t)sFlag[4 + x] + 0.5) * (1.0 / 4294967296.0);
         acc_ok = u < exp(gamma * (ll - curr));
         better = acc_ok && ll > best;
         if (p.trace != nullptr) {
@@ -216,6 +243,8 @@ __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
         ++n_acc;
       }
       __syncthreads();  // edge counts read sCurr before it is overwritten
+      const int *sProp = slot_prop(x);
+      const uint32_t *sRows = slot_rows(x);
       for (int i = tid; i < S; i += kThreads) {
         const int v = sProp[i];
         sOrder[i] = v;
@@ -228,6 +257,8 @@ __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
       }
     }
     __syncthreads();
+    // the successor that matches the decision becomes the proposal being scored; the other two slots are free
+    if (flag & 1) { const int o = x; x = sa; sa = o; } else { const int o = x; x = sr; sr = o; }
   }
   // ---- write the chain state back -----------------------------------------------------------------------
   if (counts != nullptr) {
@@ -249,7 +280,6 @@ __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
   }
 }
 
-constexpr int kFixedSmem = 16384 + 1024 + 512 + 512 + 256 + 256 + 128 + 64;
 
 }  // namespace
 
@@ -286,8 +316,9 @@ int launch_mcmc_fused(const nemb200_dataset *h, int n, int64_t n_iters, int64_t 
     NEMB_CHECK_CUDA(cudaFuncSetAttribute(k_mcmc_fused<TW_, EPT_, THR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_mcmc_fused<TW_, EPT_, THR_><<<n, THR_, smem, st>>>(p);                                                                   \
   } while (0)
-  if (h->W == 1) { if (one) NEMB_FUSED(1, 1, 256); else NEMB_FUSED(1, 2, 512); }
-  else { if (one) NEMB_FUSED(2, 1, 256); else NEMB_FUSED(2, 2, 512); }
+  const bool tiny = h->E <= 192;  // 192 scorer threads cover it: the smallest CTA has the cheapest barriers
+  if (h->W == 1) { if (tiny) NEMB_FUSED(1, 1, 256); else if (one) NEMB_FUSED(1, 1, 320); else NEMB_FUSED(1, 2, 576); }
+  else { if (tiny) NEMB_FUSED(2, 1, 256); else if (one) NEMB_FUSED(2, 1, 320); else NEMB_FUSED(2, 2, 576); }
 #undef NEMB_FUSED
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
