@@ -143,8 +143,9 @@ int nemb200_order_to_graph(const int32_t *d_orders, int n_chains, int S, int rul
  *        d_gamma       f64   [n]         per-chain inverse temperature (gamma of :224-229)
  *      iter0: global index of the first iteration (RNG counter / burn-in bookkeeping);
  *      resume == 0 scores the start orders first (method(), :258).
- *      score_impl: NEMB200_SCORE_AUTO picks the persistent fused kernel for small problems (S*E <= 1e5,
- *      n_chains <= 296) and the CUDA-graph loop around the tensor-core score otherwise.
+ *      score_impl: NEMB200_SCORE_AUTO picks the persistent one-CTA-per-chain kernel where it is expected to be
+ *      faster (small S*E, from a measured cost model of both paths; the chains run in waves when they do not all
+ *      fit on the GPU at once) and the CUDA-graph loop around the tensor-core score otherwise.
  *      d_workspace: nemb200_mcmc_workspace_bytes(h, n_chains) bytes. */
 size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_chains);
 int nemb200_mcmc_run(const nemb200_dataset *h, int n_chains, int64_t n_iters, int64_t iter0,

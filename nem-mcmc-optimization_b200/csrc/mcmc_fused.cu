@@ -288,10 +288,17 @@ bool mcmc_fused_supported(const nemb200_dataset *h) { return h->lut_valid && h->
 
 bool mcmc_fused_preferred(const nemb200_dataset *h, int n_chains) {
   if (!mcmc_fused_supported(h)) return false;
-  // one CTA per chain must be resident at once and one CTA-iteration must be short next to the ~25 us of
-  // launches the three-kernel loop pays per iteration
+  if ((size_t)h->E * h->W * 4 > 96 * 1024) return false;  // the bit columns of D must fit in shared memory
+  // Measured model (tools/mcmc_crossover.py, us per iteration of all chains): a CTA-iteration of the persistent kernel costs
+  // 1.5 + 0.085 per 1000 (site, E-gene) pairs and the 148 SMs take the chains in waves (two CTAs per SM share it); the
+  // three-kernel loop pays ~25 us of launches per iteration plus the tensor-core score of the batch.  Chains are
+  // independent, so the persistent kernel does not need all of them resident at once.
   const double lookups = (double)h->S * h->E;
-  return n_chains <= 2 * 148 && lookups <= 1.0e5;
+  const double share = h->E <= 256 ? 3.0 : 1.0;  // the small (256/320-thread) CTAs overlap about three deep on an SM
+  const double waves = ceil(n_chains / 148.0) / share;
+  const double fused = (1.5 + 0.085e-3 * lookups) * (waves > 1.0 ? waves : 1.0);
+  const double loop = 25.0 + (double)n_chains * lookups * 1.5e-7;
+  return fused < loop;
 }
 
 int launch_mcmc_fused(const nemb200_dataset *h, int n, int64_t n_iters, int64_t iter0, int64_t burn_in, const double *d_gamma,

@@ -640,8 +640,9 @@ def test_score_batch_split_over_launch_limit(nb):
 
 
 def test_sorted_egenes_and_multichain_loop_path(nb):
-    """Dataset(sort_egenes=True) is score-invariant; > 296 chains take the CUDA-graph loop even for a small
-    problem and agree with the persistent kernel chain by chain (same global chain ids)."""
+    """Dataset(sort_egenes=True) is score-invariant; the CUDA-graph loop around the tensor-core score and the
+    persistent kernel (which takes more chains than fit on the GPU at once in waves) agree chain by chain (same
+    global chain ids)."""
     S, E = 16, 500
     _, _, D = orc.synth_dataset(S, E, seed=9)
     A, B = orc.nem_constants(0.05, 0.1)
@@ -653,11 +654,15 @@ def test_sorted_egenes_and_multichain_loop_path(nb):
     n = 320
     orders0 = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
     ds = nb.Dataset(D, A, B)
-    loop = ds.run_chains(orders0, 64, 0.1, seed=3).result()            # auto -> loop (n > 296)
-    fused = ds.run_chains(orders0[:64], 64, 0.1, seed=3).result()       # auto -> persistent kernel
+    loop = ds.run_chains(orders0, 64, 0.1, seed=3, impl="lut").result()  # the three-kernel loop
+    fused = ds.run_chains(orders0[:64], 64, 0.1, seed=3).result()         # auto -> persistent kernel
     assert np.array_equal(loop.curr_orders[:64], fused.curr_orders)
     assert np.array_equal(loop.accept_counts[:64], fused.accept_counts)
     assert np.allclose(loop.best_scores[:64], fused.best_scores, rtol=1e-12)
+    waves = ds.run_chains(orders0, 64, 0.1, seed=3).result()              # auto: 320 chains > 296 resident CTAs, still fused
+    assert np.array_equal(waves.curr_orders, loop.curr_orders)
+    assert np.array_equal(waves.accept_counts, loop.accept_counts)
+    assert np.array_equal(waves.edge_counts, loop.edge_counts)
 
 
 def test_mcmc_two_group_overlap_equals_separate_runs(nb):
