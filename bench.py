@@ -33,11 +33,15 @@ WORKLOAD = "BASELINE config 3: S=50 x E=10000 synthetic NEM (rnd_dag_gen edge la
 
 
 def peaks():
+    """-> (bf16 burst TFLOP/s, bf16 sustained TFLOP/s, HBM GB/s, source).  The score kernel is timed ALONE (a few ms of
+    back-to-back launches at full clocks), so the burst figure is its roofline denominator; the sustained figure is
+    reported beside it (B200_PROFILING.md)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        burst = d.get("bf16_tflops", d.get("bf16_tflops_sustained"))
+        return burst, d.get("bf16_tflops_sustained", burst), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json: burst bf16 for a kernel timed alone)"
+    return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(threading.Thread):
@@ -72,29 +76,81 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------ CPU arm (oracle)
-def _cpu_worker(args):
-    from oracle import nem_oracle as orc
-    graphs, D, A, B = args
-    return [orc.score_matrix(orc.closure_pathcount(g), D, A, B) for g in graphs]
+# ------------------------------------------------------------------------------------ CPU arm
+# kind "reference": the reference's OWN functions (utils.ancestor + get_reduced_score_tables + compute_ll_ratios +
+# calculate_ll, driven as nem.py:132-142) from the unmodified modules staged in oracle/_ref/ (oracle/ref_stage.py);
+# kind "port": the numpy restatement in oracle/nem_oracle.py (adj^T @ T + logaddexp, 5-8x faster).
+# The scorer and the graphs are module globals set BEFORE the workers fork, so nothing but index ranges and
+# scores crosses a pipe inside the timed region.
+_CPU = {}
 
 
-def cpu_arm(D, A, B, graphs, cores):
-    """The reference's numpy path (utils.ancestor + U + Phi^T T + logaddexp.reduce, restated in
-    oracle/nem_oracle.py) fanned out over `cores` processes; returns graph-scores/s."""
-    import multiprocessing as mp
-    try:
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(1)
-    except Exception:
-        pass
-    chunks = [graphs[i::cores] for i in range(cores)]
-    with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_worker, [(c[:1], D, A, B) for c in chunks])  # warm the workers
+def _cpu_worker(span):
+    lo, hi = span
+    fn, graphs = _CPU["fn"], _CPU["graphs"]
+    return [fn(graphs[g]) for g in range(lo, hi)]
+
+
+def cpu_kind():
+    from oracle import ref_stage
+    return "reference" if ref_stage.staged() else "port"
+
+
+class CpuArm:
+    """A pool of forked workers that score graphs of one dataset with the reference (or the port)."""
+
+    def __init__(self, D, A, B, graphs, cores, kind):
+        import multiprocessing as mp
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(1)   # one numpy thread per worker process
+        except Exception:
+            pass
+        if kind == "reference":
+            from oracle import ref_driver
+            scorer = ref_driver.RefScorer(D, A, B)       # S tables of S x E float64, built once (nem.py:49-64)
+            fn = scorer.score
+        else:
+            from oracle import nem_oracle as orc
+            fn = lambda g: orc.score_matrix(orc.closure_pathcount(g), D, A, B)
+        _CPU["fn"], _CPU["graphs"] = fn, graphs
+        self.cores, self.kind = cores, kind
+        self.pool = mp.get_context("fork").Pool(cores)    # forked after the globals exist: tables are shared copy-on-write
+        self.pool.map(_cpu_worker, [(i, i + 1) for i in range(min(cores, len(graphs)))])  # warm every worker
+
+    def run(self, lo, hi):
+        """Scores graphs[lo:hi] over all workers; -> (seconds, scores)."""
+        n, c = hi - lo, self.cores
+        spans = [(lo + n * i // c, lo + n * (i + 1) // c) for i in range(c)]
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(c, D, A, B) for c in chunks])
+        parts = self.pool.map(_cpu_worker, spans, chunksize=1)
         dt = time.perf_counter() - t0
-    return len(graphs) / dt, dt
+        return dt, [x for p in parts for x in p]
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline_leg(D, A, B, cores, budget_s=12.0):
+    """cpu_baseline of the GPU arm: a bounded sample (~budget_s of CPU work per kind) of the same sweep."""
+    out = None
+    for kind in (["reference"] if cpu_kind() == "reference" else []) + ["port"]:
+        graphs = unclosed_graphs(CHAINS, 1)
+        arm = CpuArm(D, A, B, graphs, cores, kind)
+        dt0, _ = arm.run(0, 2 * cores)                                  # rate estimate
+        n = int(min(max(2 * cores / dt0 * budget_s, 2 * cores), CHAINS))
+        dt, _ = arm.run(0, n)
+        arm.close()
+        row = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n} of the {CHAINS} graphs of one sweep (closure + score) over {cores} forked processes, {dt:.1f} s; "
+                         + ("the reference's own utils.ancestor + NEM.get_reduced_score_tables + compute_ll_ratios + calculate_ll (oracle/_ref)"
+                            if kind == "reference" else "numpy restatement of the reference (oracle/nem_oracle.py: adj^T @ T + logaddexp)")}
+        if out is None:
+            out = row
+        else:
+            out["port"] = row
+    return out
 
 
 def unclosed_graphs(n, seed):
@@ -249,7 +305,7 @@ def config5_sweep(nb, synth):
     ev[1].record()
     torch.cuda.synchronize()
     t_big = ev[0].elapsed_time(ev[1]) / 5
-    hbm = peaks()[1]
+    hbm = peaks()[2]
     big_gbs = 2.0 * s * 4 * 16 * n / (t_big * 1e-3) / 1e9
     return {"graphs": n, "closure_1M_graphs_ms": t_big, "closure_1M_graphs_GBps": big_gbs,
             "closure_1M_graphs_hbm_frac": big_gbs / hbm if hbm else None, "closure_ms": t_c, "score_ms": t_s, "closures_per_s": n / (t_c * 1e-3), "graph_scores_per_s": n / (t_s * 1e-3),
@@ -257,29 +313,55 @@ def config5_sweep(nb, synth):
             "score_tflops_algorithmic": 2.0 * s * s * e * n / (t_s * 1e-3) / 1e12}
 
 
+def workload_config(world):
+    """The `config` object: identical in both arms (the reference arm runs the same sweep on the host cores)."""
+    batch_bytes = CHAINS * S * ((S + 31) // 32) * 4
+    n_batches = (160 << 20) // batch_bytes + 1
+    return {"workload": WORKLOAD, "S": S, "E": E, "graphs_per_step_per_gpu": CHAINS,
+            "l2": f"{n_batches} distinct input batches rotated ({n_batches * batch_bytes >> 20} MiB"
+                  f"{' > 126 MB L2' if n_batches * batch_bytes > (126 << 20) else ''}); the 1.3 MB operand image of D is "
+                  "reused every step by design (SURVEY 8d)",
+            "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"}, n_batches, batch_bytes
+
+
 def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref when staged, else the port)
+    on all host cores.  A step = the SAME sweep as the GPU arm's step: closure + score of 1024 candidate graphs (no
+    extrapolation; only if the whole run would exceed ~5 minutes is a step cut to a stated sample of the sweep)."""
     if rank != 0:
         return
     from nem_b200 import synth
     cores = os.cpu_count() or 1
     _, _, D = synth.dataset(S, E, seed=0, alpha=ALPHA, beta=BETA)
     A, B = synth.nem_constants(ALPHA, BETA)
-    per_step = max(4 * cores, 64)  # bounded sample of the 1024-graph sweep
-    graphs = unclosed_graphs(per_step, 1)
-    for _ in range(min(args.warmup, 1)):
-        cpu_arm(D, A, B, graphs[:cores], cores)
-    t, n = 0.0, 0
-    for k in range(args.steps):
-        _, dt = cpu_arm(D, A, B, graphs, cores)
+    kind = cpu_kind()
+    K, Wm = args.steps, args.warmup
+    n_rot = 4                                           # distinct batches, rotated like the GPU arm's inputs
+    graphs = np.concatenate([unclosed_graphs(CHAINS, 100 + b) for b in range(n_rot)])
+    arm = CpuArm(D, A, B, graphs, cores, kind)
+    dt0, _ = arm.run(0, 2 * cores)
+    rate0 = 2 * cores / dt0
+    per_step = CHAINS if CHAINS * (K + Wm) / rate0 <= args.ref_budget_s else int(max(2 * cores, rate0 * args.ref_budget_s / (K + Wm)))
+    for k in range(Wm):
+        arm.run((k % n_rot) * CHAINS, (k % n_rot) * CHAINS + per_step)
+    t = 0.0
+    for k in range(K):
+        lo = ((Wm + k) % n_rot) * CHAINS
+        dt, _ = arm.run(lo, lo + per_step)
         t += dt
-        n += per_step
-    v = n / t
-    sample = f"{per_step} of the {CHAINS} graphs of one sweep per step (closure + score), numpy port of the reference over {cores} processes"
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps) * CHAINS / per_step,
+    arm.close()
+    v = per_step * K / t
+    what = ("the reference's own utils.ancestor + NEM.get_reduced_score_tables + compute_ll_ratios + calculate_ll (unmodified nem.py / utils.py staged in oracle/_ref)"
+            if kind == "reference" else "numpy restatement of the reference (oracle/nem_oracle.py); oracle/_ref not staged")
+    sample = (f"every step = {per_step} of the {CHAINS} graphs of one sweep (closure + score), {what}, {cores} forked processes")
+    cfg, _, _ = workload_config(args.gpus)
+    if per_step != CHAINS:
+        cfg = dict(cfg, reference_step_sample=per_step)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                      "warmup": Wm, "ms_per_step": 1e3 * t / max(1, K),
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "sample": sample},
-                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "config": cfg,
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -302,8 +384,7 @@ def run_gpu(args, rank, world, local_rank):
     W = ds.W
 
     # ---- inputs: rotating batches of unclosed candidate graphs, in total larger than the 126 MB L2
-    batch_bytes = CHAINS * S * W * 4
-    n_batches = (160 << 20) // batch_bytes + 1
+    cfg, n_batches, batch_bytes = workload_config(world)
     host_bits = torch.empty((n_batches, CHAINS, S, W), dtype=torch.int32).pin_memory()
     one = nb.pack_adj(unclosed_graphs(CHAINS, 100 + rank)).view(np.int32)
     rng = np.random.default_rng(rank)
@@ -350,7 +431,11 @@ def run_gpu(args, rank, world, local_rank):
         for k in range(Wm):
             sweep(dev_bits[k % n_batches])
     sampler.start()
-    ms_value = timed(lambda k: sweep(dev_bits[(Wm + k) % n_batches]), K)
+    # `value`: the median of REPEATS consecutive blocks of exactly K steps (a 20-step block lasts ~2 ms, so single
+    # blocks carry launch jitter; every block is bracketed by barrier + synchronize like the contract's timed region)
+    REPEATS = 5
+    blocks_value = sorted(timed(lambda k, r=r: sweep(dev_bits[(Wm + r * K + k) % n_batches]), K) for r in range(REPEATS))
+    ms_value = blocks_value[REPEATS // 2]
     # ---- dominant kernel alone (score + its finalize), for the roofline line
     with torch.cuda.stream(stream):
         nb._lib.check(L.nemb200_closure_u32(C.c_void_p(dev_bits[0].data_ptr()), CHAINS, S, C.c_void_p(closed.data_ptr()), sp))
@@ -358,7 +443,8 @@ def run_gpu(args, rank, world, local_rank):
     def score_only(k):
         nb._lib.check(L.nemb200_score_batch(ds._h, C.c_void_p(closed.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
                                             C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
-    ms_kernel = timed(score_only, K) / K
+    blocks_kernel = sorted(timed(score_only, K) / K for r in range(REPEATS))
+    ms_kernel = blocks_kernel[REPEATS // 2]
     # the opt-in pair-merged table kernel (two attachment sites per look-up): planner + score, same batch
     ms_pair = None
     if ds.S >= 33 and ds.S <= 52 and ds.lut_valid and "pair" not in os.environ.get("BENCH_SKIP", ""):
@@ -421,25 +507,25 @@ def run_gpu(args, rank, world, local_rank):
     acc_rate = float(state.accept.sum().item()) / (state.n * state.iters_done)
 
     if rank == 0:
-        tf_peak, hbm_peak, how = peaks()
+        tf_peak, tf_sustained, hbm_peak, how = peaks()
         flops = 2.0 * S * S * E * CHAINS
         achieved = flops / (ms_kernel * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("score_kernel_dram_bytes_per_launch")
+        if os.path.exists(tp):   # dram__bytes_read+write of ONE ncu --set full capture of this kernel (not measured live)
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("score_kernel_dram_bytes_per_launch"), tj.get("source", "profiles/traffic.json (committed ncu capture)")
         out = {
             "metric": METRIC, "value": CHAINS * world * K / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 x u8 -> s32 MMA (exact counts), f32 logsumexp, f64 sums", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "S": S, "E": E, "graphs_per_step_per_gpu": CHAINS,
-                       "score_impl": "lut" if ds.lut_valid else "ex2",
-                       "l2": f"{n_batches} distinct input batches rotated ({n_batches * batch_bytes >> 20} MiB"
-                             f"{' > 126 MB L2' if n_batches * batch_bytes > (126 << 20) else ''}); the 1.3 MB operand image of D is "
-                             "reused every step by design (SURVEY 8d)",
-                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+            "config": cfg,
+            "timing": {"repeats": REPEATS, "block_steps": K, "value_block_ms": blocks_value, "kernel_ms_blocks": blocks_kernel,
+                       "rule": "median of the repeats; each block = exactly K steps between barrier + synchronize"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                         "traffic": traffic, "kernel": "k_score_tc (tcgen05 kind::i8 + fused logsumexp)",
+                         "peak_sustained": tf_sustained, "frac_sustained": achieved / tf_sustained,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_score_tc (tcgen05 kind::i8 + fused logsumexp)",
+                         "score_impl": ds.auto_impl_name() if hasattr(ds, "auto_impl_name") else ("lut" if ds.lut_valid else "ex2"),
                          "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": flops,
                          "exps_per_launch": float((S + 1) * E * CHAINS), "peak_source": how,
                          # what actually limits the kernel: one shared-memory look-up per (site, E-gene),
@@ -469,13 +555,7 @@ def run_gpu(args, rank, world, local_rank):
             if "config4" not in os.environ.get("BENCH_SKIP", ""):
                 out["config4_shape"] = config4_shape_leg(nb, synth)
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            v0, _ = cpu_arm(D, A, B, unclosed_graphs(2 * cores, 2), cores)   # rate estimate
-            n_sample = int(min(max(v0 * 10.0, 2 * cores), 8192))               # ~10 s of CPU work
-            v, dt = cpu_arm(D, A, B, unclosed_graphs(n_sample, 1), cores)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"{n_sample} graphs of the same sweep (closure + score), numpy port of the reference "
-                                             f"over {cores} processes, {dt:.1f} s"}
+            out["cpu_baseline"] = cpu_baseline_leg(D, A, B, os.cpu_count() or 1)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -489,6 +569,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0,
+                    help="--impl reference: a step is the full 1024-graph sweep unless steps+warmup of them would take longer than this; "
+                         "then every step is a stated sample of the sweep")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

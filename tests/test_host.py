@@ -158,12 +158,34 @@ def test_gloo_world_size_2(tmp_path):
 def test_bench_reference_arm_runs_on_cpu():
     """`bench.py --impl reference` (the CPU arm the driver launches) prints one JSON line with the contract keys."""
     import json
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-budget-s", "3"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == "nem_graph_scores_per_s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    from oracle import ref_stage
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_stage.staged() else "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+    # same workload description as the GPU arm, no extrapolated step time
+    assert d["config"]["S"] == 50 and d["config"]["E"] == 10000 and d["config"]["graphs_per_step_per_gpu"] == 1024
+    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - d["config"].get("reference_step_sample", 1024)) < 1e-6 * 1024
+
+
+def test_reference_driver_matches_port_and_goldens():
+    """oracle/_ref (the reference's own nem.py / utils.py, staged by oracle/ref_stage.py) driven as nem.py:132-142
+    gives the same scores as the numpy restatement; skipped when the reference is not staged."""
+    import pytest
+    from oracle import ref_stage, nem_oracle as orc
+    if not ref_stage.staged():
+        pytest.skip("oracle/_ref not staged")
+    from oracle import ref_driver
+    _, _, D = orc.synth_dataset(12, 150, seed=3)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rs = ref_driver.RefScorer(D, A, B)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        g = np.triu(rng.random((12, 12)) < 0.3, 1).astype(np.uint8)
+        a, b = rs.score(g), orc.score_matrix(orc.closure_bool(g), D, A, B)
+        assert abs(a - b) <= 1e-11 * abs(b)
 
 
 def test_score_kernel_partition_invariants():
