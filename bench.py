@@ -505,6 +505,20 @@ def run_gpu(args, rank, world, local_rank):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     acc_rate = float(state.accept.sum().item()) / (state.n * state.iters_done)
+    # parity of the timed run: chain 0 of rank 0 against the C oracle's restatement of nem_order_mcmc.py:272-302 over
+    # ALL iterations this state has run (same Philox stream): accept count, current order, best graph, scores
+    mcmc_check = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import c_oracle
+        ref = c_oracle.mcmc_chain(D, A, B, orders0[0], state.iters_done, 2.0 * S / E, swap_prob=0.95, seed=1234, chain=0,
+                                  rule=1, cand=cand, use_nem=True)
+        got_order = state.orders[0].cpu().numpy()
+        got_best = nb.unpack_adj(state.best_bits[:1].cpu().numpy().view(np.uint32), S)[0]
+        ok = (int(state.accept[0].item()) == ref["n_accept"] and np.array_equal(got_order, ref["curr_order"])
+              and np.array_equal(got_best, ref["best_graph"])
+              and abs(float(state.best_scores[0].item()) - ref["best_score"]) <= 1e-6 * abs(ref["best_score"]))
+        assert ok, "order-MCMC run differs from the oracle chain"
+        mcmc_check = {"chain": 0, "iterations": state.iters_done, "accepts": ref["n_accept"], "equal_to_oracle": bool(ok)}
 
     if rank == 0:
         tf_peak, tf_sustained, hbm_peak, how = peaks()
@@ -542,7 +556,7 @@ def run_gpu(args, rank, world, local_rank):
             "mcmc": {"value": state.n * world * mc_iters / (ms_mcmc * 1e-3), "unit": "chain-iterations/s", "iters": mc_iters,
                      "chains": state.n * world, "ms_per_iter": ms_mcmc / mc_iters, "accept_rate": acc_rate,
                      "rule": "masked+closure", "collectives": "edge-count all-reduce + best-graph broadcast, once per run",
-                     "best_score": best[0], "edge_count_total": int(counts.sum().item())},
+                     "best_score": best[0], "edge_count_total": int(counts.sum().item()), "oracle_check": mcmc_check},
             "clocks": sampler.summary(),
         }
         if ms_pair is not None:

@@ -15,7 +15,12 @@
  *    (dag[a][b]==1 iff a->b, nem_order_mcmc.py:213,220); the score ignores the diagonal (it uses I|Phi),
  *    the closure treats it like any other entry;
  *  - orders are int32[S] position -> S-gene label (the reference's perm_order, :29-48);
- *  - S <= 128 (tensor-core path), E arbitrary.
+ *  - S <= 128 (tensor-core path), E arbitrary;
+ *  - threads: a dataset handle is immutable after nemb200_dataset_create; the little host state the launchers keep
+ *    (completion-counter assignment of score workspaces, the cached CUDA graph of the MCMC loop) sits behind a mutex
+ *    inside the handle, so several host threads may call nemb200_score_batch on one handle as long as each uses its
+ *    OWN score workspace and stream (launches that share a workspace must be stream-ordered); nemb200_mcmc_run
+ *    calls on one handle are serialised.  nemb200_dataset_destroy must not race with any other call.
  */
 #ifndef NEMB200_H
 #define NEMB200_H
@@ -161,11 +166,22 @@ int nemb200_mcmc_run(const nemb200_dataset *h, int n_chains, int64_t n_iters, in
  *      replica_exchange_step (nem_order_mcmc.py:326-340).  Chains are grouped in ladders of
  *      `ladder` consecutive chains; phase 0 pairs (0,1),(2,3).., phase 1 pairs (1,2),(3,4)..;
  *      swap iff u < exp(-delta), delta as :333.  States (order, graph, score) are exchanged,
- *      gammas stay.  Philox counter (round, ladder id, 1). */
+ *      gammas stay.  The uniform of pair k of ladder l is (r3 + 0.5) / 2^32 of Philox4x32-10 with key = seed and
+ *      counter (round lo, round hi, l * (ladder / 2) + k, 1). */
 int nemb200_replica_exchange(int n_chains, int ladder, int phase, int64_t round, uint64_t seed,
                              int S, const double *d_gamma, int32_t *d_orders,
                              double *d_curr_scores, uint32_t *d_curr_bits, int64_t *d_n_swaps,
                              void *stream);
+/* the same with the reference's own swap criterion: replica_exchange_step takes scores[i] =
+ * replicas[i].best_score (nem_order_mcmc.py:321), i.e. the best score each replica reached in the round that
+ * just ended (method() restarts best_score from the current score, :259-260), puts them into delta (:333) and
+ * swaps WHOLE replica objects (:335): current state and best state change places, scores[] with them (:336).
+ * Same pairing, same Philox counter as above. */
+int nemb200_replica_exchange_best(int n_chains, int ladder, int phase, int64_t round, uint64_t seed,
+                                  int S, const double *d_gamma, int32_t *d_orders,
+                                  double *d_curr_scores, uint32_t *d_curr_bits, double *d_best_scores,
+                                  int32_t *d_best_orders, uint32_t *d_best_bits, int64_t *d_n_swaps,
+                                  void *stream);
 
 /* ---- device-side data synthesis: replaces utils.create_real_knockdown_mat (utils.py:15-23) and
  *      utils.create_observed_knockdown_mat (utils.py:25-35) for large shapes.  d_adj_bits: the (closed) true

@@ -7,18 +7,23 @@ namespace {
 
 // cell[i][e] = U[i][e] + sum_j log(1 - w_ij + w_ij * exp(T[j][e]))  with T two-valued (nem.py:46):
 // the log term is l1_ij where D[j][e]==1 and l0_ij where 0; U[i][e] = T[i][e] + N[e], U[S][e] = N[e].
+// blockIdx.y selects a chunk of kCellRows child rows i: a CTA stages only its rows of the two S x S tables
+// (2 * 48 * 128 * 8 B = 96 KB at S = 128; the whole tables would need 256 KB, more than a CTA can have)
+constexpr int kCellRows = 48;
 __global__ void __launch_bounds__(128) k_cell_ratios(const uint32_t *__restrict__ dcol, int S, int W, int E, double A, double B,
                                                      const double *__restrict__ weights, int apply_expit,
                                                      double *__restrict__ cell) {
-  extern __shared__ double sh[];  // l0[S*S], l1[S*S]
-  double *l0 = sh, *l1 = sh + S * S;
+  extern __shared__ double sh[];  // l0[rows*S], l1[rows*S]
+  const int i_lo = blockIdx.y * kCellRows, i_hi = min(S, i_lo + kCellRows), rows = i_hi - i_lo;
+  double *l0 = sh, *l1 = sh + rows * S;
   const double eA = exp(-A), eB = exp(B);
-  for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
-    double w = weights[i];
-    bool present = w != 0.0 && (i / S) != (i % S);
+  for (int k = threadIdx.x; k < rows * S; k += blockDim.x) {
+    const int i = i_lo + k / S, j = k % S;
+    double w = weights[i * S + j];
+    bool present = w != 0.0 && i != j;
     if (apply_expit && present) w = 1.0 / (1.0 + exp(-w));  // the reference's MCMC driver quirk
-    l0[i] = present ? log(1.0 - w + w * eB) : 0.0;
-    l1[i] = present ? log(1.0 - w + w * eA) : 0.0;
+    l0[k] = present ? log(1.0 - w + w * eB) : 0.0;
+    l1[k] = present ? log(1.0 - w + w * eA) : 0.0;
   }
   __syncthreads();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -27,12 +32,13 @@ __global__ void __launch_bounds__(128) k_cell_ratios(const uint32_t *__restrict_
   int ones = 0;
   for (int w = 0; w < W; ++w) { d[w] = dcol[(size_t)e * W + w]; ones += __popc(d[w]); }
   const double N = A * ones;
-  for (int i = 0; i < S; ++i) {
+  for (int i = i_lo; i < i_hi; ++i) {
     double v = N + (((d[i >> 5] >> (i & 31)) & 1u) ? -A : B);
-    for (int j = 0; j < S; ++j) v += ((d[j >> 5] >> (j & 31)) & 1u) ? l1[i * S + j] : l0[i * S + j];
+    const double *r0 = l0 + (i - i_lo) * S, *r1 = l1 + (i - i_lo) * S;
+    for (int j = 0; j < S; ++j) v += ((d[j >> 5] >> (j & 31)) & 1u) ? r1[j] : r0[j];
     cell[(size_t)i * E + e] = v;
   }
-  cell[(size_t)S * E + e] = N;
+  if (blockIdx.y == 0) cell[(size_t)S * E + e] = N;
 }
 
 // per-column logaddexp.reduce over `rows` rows, optional posterior weights exp(cell - colsum), block partial sums
@@ -72,10 +78,12 @@ __global__ void k_sum_partials(const double *partial, int n, double *out) {
 extern "C" int nemb200_cell_ratios(const nemb200_dataset *h, const double *d_weights, int apply_expit, double *d_cell,
                                    void *stream) {
   NEMB_REQUIRE(h && d_weights && d_cell, "null argument");
-  size_t smem = sizeof(double) * 2 * h->S * h->S;
+  const int rows = h->S < kCellRows ? h->S : kCellRows;
+  size_t smem = sizeof(double) * 2 * rows * h->S;
   NEMB_CHECK_CUDA(cudaFuncSetAttribute(k_cell_ratios, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_cell_ratios<<<(h->E + 127) / 128, 128, smem, (cudaStream_t)stream>>>(h->dcol, h->S, h->W, h->E, h->A, h->B, d_weights,
-                                                                        apply_expit, d_cell);
+  dim3 grid((h->E + 127) / 128, (h->S + kCellRows - 1) / kCellRows);
+  k_cell_ratios<<<grid, 128, smem, (cudaStream_t)stream>>>(h->dcol, h->S, h->W, h->E, h->A, h->B, d_weights,
+                                                          apply_expit, d_cell);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/nemb200.h"
 
 #define NEMB200_LOG2E 1.4426950408889634074
@@ -15,6 +17,23 @@
 #define NEMB200_LUTM_ZERO 8190   // entry that is 0 at every level (n = 127 > S): what padding columns look up
 
 // ---- host handle ---------------------------------------------------------------------------
+// The handle itself is immutable after nemb200_dataset_create.  The few pieces of host state the launchers keep
+// between calls (which score workspace owns which completion counter, the cached CUDA graph of the MCMC iteration
+// body, the side stream of the two-group loop) live in this separate object behind a mutex, so a `const
+// nemb200_dataset *` is never cast: several host threads may score through one handle; nemb200_mcmc_run calls on
+// one handle are serialised by the mutex.
+struct nemb200_cache {
+  std::recursive_mutex mu;  // recursive: nemb200_mcmc_run holds it while its steps call the score launcher
+  const void *ctr_ws[64] = {};  // which score workspace owns which completion counter (counters live in the dataset
+  int n_ctr = 0;                // workspace: library-initialised memory, zero at rest, whatever the caller allocates)
+  // one cached CUDA graph of the MCMC iteration body (re-used while the same buffers are passed)
+  unsigned long long mcmc_graph_key = 0;
+  void *mcmc_graph_exec = nullptr;  // cudaGraphExec_t
+  // second capture branch of the two-group MCMC loop (created on first use, destroyed with the handle)
+  void *mcmc_side_stream = nullptr;                      // cudaStream_t
+  void *mcmc_ev_fork = nullptr, *mcmc_ev_join = nullptr; // cudaEvent_t
+};
+
 struct nemb200_dataset {
   int S, E, W;        // S-genes, E-genes, words per bit row
   int KA;             // 64-element K atoms (bf16, SWIZZLE_128B rows of 128 B)
@@ -43,14 +62,7 @@ struct nemb200_dataset {
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)
   double *sumN;       // [1] A * sum(D)   (nem.py:62 summed over e)
   int *counters;      // [64] self-resetting completion counters of the score kernel's fused finalize (zero at rest)
-  const void *ctr_ws[64];  // host: which score workspace owns which counter
-  int n_ctr;
-  // one cached CUDA graph of the MCMC iteration body (re-used while the same buffers are passed)
-  unsigned long long mcmc_graph_key;
-  void *mcmc_graph_exec;  // cudaGraphExec_t
-  // second capture branch of the two-group MCMC loop (created on first use, destroyed with the handle)
-  void *mcmc_side_stream;            // cudaStream_t
-  void *mcmc_ev_fork, *mcmc_ev_join; // cudaEvent_t
+  nemb200_cache *cache;  // mutable launcher state (see above); owned by the handle
 };
 
 void nemb200_set_error(const char *fmt, ...);

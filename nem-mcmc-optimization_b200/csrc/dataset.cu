@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -170,6 +172,8 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   cudaStream_t st = (cudaStream_t)stream;
   nemb200_dataset *h = (nemb200_dataset *)calloc(1, sizeof(nemb200_dataset));
   NEMB_REQUIRE(h != nullptr, "out of host memory");
+  h->cache = new (std::nothrow) nemb200_cache();
+  if (h->cache == nullptr) { free(h); nemb200_set_error("out of host memory"); return -1; }
   uint8_t *base = (uint8_t *)d_workspace;
   h->S = S; h->E = E; h->W = L.W; h->KA = 1; h->n_mtiles = L.n_mtiles;
   h->CS = S;  // set below once the epilogue kind is known
@@ -194,7 +198,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   h->G = h->G >= 4 ? (h->G & ~3) : 2;           // epilogue warpgroup), or 2 for S > 64
   h->G_lut = h->G;  // the specialised table kernel may use its own tile width (score_tc.cu: tile_graphs)
   int E_pad = L.n_mtiles * 128;
-  if (cudaMemsetAsync(h->counters, 0, 64 * sizeof(int), st) != cudaSuccess) { free(h); nemb200_set_error("cudaMemsetAsync failed"); return -2; }
+  if (cudaMemsetAsync(h->counters, 0, 64 * sizeof(int), st) != cudaSuccess) { delete h->cache; free(h); nemb200_set_error("cudaMemsetAsync failed"); return -2; }
   k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
   k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 0, h->a_lut);
   h->pair_ok = h->lut_valid && pair_supported(S);
@@ -226,6 +230,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   k_build_lut<<<16, 256, 0, st>>>(S, h->alpha2, h->beta2, (double)h->scale, h->lut, h->tabs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
+    delete h->cache;
     free(h);
     nemb200_set_error("dataset kernels failed to launch: %s", cudaGetErrorString(e));
     return -2;
@@ -235,10 +240,14 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
 }
 
 extern "C" int nemb200_dataset_destroy(nemb200_dataset *h) {
-  if (h && h->mcmc_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->mcmc_graph_exec);
-  if (h && h->mcmc_ev_fork) cudaEventDestroy((cudaEvent_t)h->mcmc_ev_fork);
-  if (h && h->mcmc_ev_join) cudaEventDestroy((cudaEvent_t)h->mcmc_ev_join);
-  if (h && h->mcmc_side_stream) cudaStreamDestroy((cudaStream_t)h->mcmc_side_stream);
+  if (h && h->cache) {
+    nemb200_cache *c = h->cache;
+    if (c->mcmc_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->mcmc_graph_exec);
+    if (c->mcmc_ev_fork) cudaEventDestroy((cudaEvent_t)c->mcmc_ev_fork);
+    if (c->mcmc_ev_join) cudaEventDestroy((cudaEvent_t)c->mcmc_ev_join);
+    if (c->mcmc_side_stream) cudaStreamDestroy((cudaStream_t)c->mcmc_side_stream);
+    delete c;
+  }
   free(h);
   return 0;
 }

@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_mcmc_flush(int n, int S
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_replica_exchange(
     int n_chains, int ladder, int phase, long long round, uint64_t seed, int S, int W, const double *__restrict__ gamma,
     int32_t *__restrict__ orders, double *__restrict__ curr_scores, uint32_t *__restrict__ curr_bits,
-    long long *__restrict__ n_swaps) {
+    long long *__restrict__ n_swaps, double *__restrict__ best_scores, int32_t *__restrict__ best_orders,
+    uint32_t *__restrict__ best_bits) {
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pairs_per_ladder = ladder / 2;  // upper bound; odd phases may have one fewer
   const int pid = blockIdx.x * kWarpsPerBlock + wib;
@@ -213,9 +214,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_replica_exchange(
   uint32_t ctr[4] = {(uint32_t)round, (uint32_t)((unsigned long long)round >> 32), (uint32_t)pid, 1u};
   philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
   const double u = ((double)ctr[3] + 0.5) * (1.0 / 4294967296.0);
-  const double si = curr_scores[i], sj = curr_scores[j];
+  // default: the chains' CURRENT scores (standard parallel tempering); faithful mode (best_scores != NULL): the
+  // reference's scores[i] = replicas[i].best_score (:321), and whole replicas change places (:335), best state included
+  const double si = best_scores ? best_scores[i] : curr_scores[i], sj = best_scores ? best_scores[j] : curr_scores[j];
   const double delta = gamma[i] * sj - gamma[i] * si + gamma[j] * si - gamma[j] * sj;  // :333
   if (!(u < exp(-delta))) return;
+  if (best_scores != nullptr) {
+    for (int q = lane; q < S; q += 32) {
+      int a = best_orders[(size_t)i * S + q], b = best_orders[(size_t)j * S + q];
+      best_orders[(size_t)i * S + q] = b; best_orders[(size_t)j * S + q] = a;
+    }
+    for (int q = lane; q < S * W; q += 32) {
+      uint32_t a = best_bits[(size_t)i * S * W + q], b = best_bits[(size_t)j * S * W + q];
+      best_bits[(size_t)i * S * W + q] = b; best_bits[(size_t)j * S * W + q] = a;
+    }
+  }
   for (int q = lane; q < S; q += 32) {
     int a = orders[(size_t)i * S + q], b = orders[(size_t)j * S + q];
     orders[(size_t)i * S + q] = b; orders[(size_t)j * S + q] = a;
@@ -226,7 +239,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_replica_exchange(
   }
   __syncwarp();
   if (lane == 0) {
-    curr_scores[i] = sj; curr_scores[j] = si;
+    const double ci = curr_scores[i], cj = curr_scores[j];
+    curr_scores[i] = cj; curr_scores[j] = ci;
+    if (best_scores != nullptr) { best_scores[i] = sj; best_scores[j] = si; }
     if (n_swaps) atomicAdd((unsigned long long *)n_swaps, 1ull);
   }
 }
@@ -333,7 +348,8 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
                              d_accept, d_edge_counts, d_score_trace, st);
   constexpr int kUnroll = 16;  // iterations per captured CUDA graph
   const int thr = kWarpsPerBlock * 32;
-  nemb200_dataset *hm = const_cast<nemb200_dataset *>(h);
+  nemb200_cache *hm = h->cache;  // graph cache + side stream: mutable launcher state, serialised per handle
+  std::lock_guard<std::recursive_mutex> lock(hm->mu);
 
   // ---- chain groups (see first_group_size)
   struct Group { int c0, n; McmcWs w; };
@@ -469,18 +485,35 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
   return 0;
 }
 
-extern "C" int nemb200_replica_exchange(int n_chains, int ladder, int phase, int64_t round, uint64_t seed, int S,
-                                        const double *d_gamma, int32_t *d_orders, double *d_curr_scores,
-                                        uint32_t *d_curr_bits, int64_t *d_n_swaps, void *stream) {
+static int replica_exchange_launch(int n_chains, int ladder, int phase, int64_t round, uint64_t seed, int S,
+                                   const double *d_gamma, int32_t *d_orders, double *d_curr_scores, uint32_t *d_curr_bits,
+                                   int64_t *d_n_swaps, double *d_best_scores, int32_t *d_best_orders,
+                                   uint32_t *d_best_bits, void *stream) {
   NEMB_REQUIRE(n_chains >= 0 && ladder >= 2 && S >= 1 && S <= NEMB200_MAX_S, "bad arguments");
   if (n_chains < 2) return 0;
   NEMB_REQUIRE(d_gamma && d_orders && d_curr_scores && d_curr_bits, "null device pointer");
   int ladders = (n_chains + ladder - 1) / ladder, pairs = ladders * (ladder / 2);
   k_replica_exchange<<<(pairs + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       n_chains, ladder, phase & 1, round, seed, S, (S + 31) / 32, d_gamma, d_orders, d_curr_scores, d_curr_bits,
-      (long long *)d_n_swaps);
+      (long long *)d_n_swaps, d_best_scores, d_best_orders, d_best_bits);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int nemb200_replica_exchange(int n_chains, int ladder, int phase, int64_t round, uint64_t seed, int S,
+                                        const double *d_gamma, int32_t *d_orders, double *d_curr_scores,
+                                        uint32_t *d_curr_bits, int64_t *d_n_swaps, void *stream) {
+  return replica_exchange_launch(n_chains, ladder, phase, round, seed, S, d_gamma, d_orders, d_curr_scores, d_curr_bits,
+                                 d_n_swaps, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int nemb200_replica_exchange_best(int n_chains, int ladder, int phase, int64_t round, uint64_t seed, int S,
+                                             const double *d_gamma, int32_t *d_orders, double *d_curr_scores,
+                                             uint32_t *d_curr_bits, double *d_best_scores, int32_t *d_best_orders,
+                                             uint32_t *d_best_bits, int64_t *d_n_swaps, void *stream) {
+  NEMB_REQUIRE(d_best_scores && d_best_orders && d_best_bits, "null device pointer");
+  return replica_exchange_launch(n_chains, ladder, phase, round, seed, S, d_gamma, d_orders, d_curr_scores, d_curr_bits,
+                                 d_n_swaps, d_best_scores, d_best_orders, d_best_bits, stream);
 }
 
 extern "C" int nemb200_edge_counts_reduce(const uint32_t *d_edge_counts, int n_chains, int S, int64_t *d_out, void *stream) {

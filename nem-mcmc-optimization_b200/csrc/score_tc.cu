@@ -28,6 +28,8 @@
 // partial sums (fused finalize).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -142,6 +144,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp (elect.sync): the idiom ptxas turns into `ELECT` + predicated issue
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -208,6 +216,21 @@ __device__ __forceinline__ float log2_split(float x) {
 }
 
 enum { EPI_LUT = 0, EPI_EX2 = 1, EPI_EX2_2PASS = 2, EPI_LUTM = 3 };
+#ifndef NEMB200_OLD_EPILOGUE
+#define NEMB200_OLD_EPILOGUE 0  // 1: the first (scalar FADD, branchy) specialised epilogue, kept for A/B timing
+#endif
+#ifndef NEMB200_LDS_BATCH
+#define NEMB200_LDS_BATCH 1  // 1: a chunk's look-ups all issue before the first is consumed (0: ptxas' own schedule, for A/B timing)
+#endif
+#ifndef NEMB200_CA
+#define NEMB200_CA 32   // lean epilogue: columns of chunk A for shares wider than 32 columns
+#endif
+#ifndef NEMB200_NA1
+#define NEMB200_NA1 12  // lean epilogue: look-ups of chunk A before the accumulator buffer is handed back
+#endif
+#ifndef NEMB200_EXP
+#define NEMB200_EXP 0  // development skip-experiments (wrong results): 1 no LDS, 2 no TMEM loads in the tile loop, 4 no log/fp64, 16 no TMA copies, 32 one MMA k-step, 64 no MMA
+#endif
 
 // Named barrier of one epilogue warpgroup (ids 1..5).  The id is an immediate on purpose: with a register operand
 // ptxas reserves all 16 hardware barriers for the kernel, and then no CTA that uses __syncthreads() (the MCMC accept
@@ -435,14 +458,19 @@ __device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const floa
 // Which attachment sites of a graph go through the exp table (true) and which through ex2.approx (false).
 // All warps of a CTA run in near lockstep, so the two kinds are interleaved in groups of four sites (a
 // float4 of biases) - otherwise the LSU and MUFU pipes would be used one after the other, not together.
-// NLUT == S_T: table only.  Otherwise every third group of four sites is an ex2 group.
+// NLUT >= S_T: table only.  Otherwise NLUT is a period P: of every P groups of four sites the last one is an ex2 group
+// (a fraction 1/P of the sites leaves the LSU pipe for the MUFU pipe).
 template <int S_T, int NLUT>
-__host__ __device__ constexpr bool is_lut_site(int j) { return NLUT >= S_T ? true : ((j >> 2) % 3) != 2; }
+__host__ __device__ constexpr bool is_lut_site(int j) { return NLUT >= S_T ? true : ((j >> 2) % NLUT) != NLUT - 1; }
+// int -> float without I2F (I2F and ex2 share the XU pipe): for 0 <= a < 2^14, (a << 9) + 0x46800000 is the bit pattern
+// of 2^14 + a; the expander folds -k1 * 2^14 into the site's bias
+constexpr uint32_t kMagic14 = 0x46800000u;
 
 // The logarithm + float64 accumulation of a finished graph is deferred (pend_*) into the next graph's
 // look-up stream so that its MUFU / F2F / DADD latency chain is off the per-tile critical path.
 struct Pending { float sum; int g; bool valid; };
 __device__ __forceinline__ void finalize_pending(Pending &pd, const Params &p, double (&part)[kMaxG / 4]) {
+  if ((NEMB200_EXP & 4) && pd.sum != 123.f) { pd.valid = false; return; }
   if (pd.valid) {
     const float l = log2_split(pd.sum) + p.scale;
 #pragma unroll
@@ -462,13 +490,13 @@ __device__ __forceinline__ void static_cols(const uint32_t (&r)[32], const float
     if (j == 0) { acc[0] = null_term; acc[1] = 0.f; acc[2] = 0.f; acc[3] = 0.f; }
     float v;
     if (is_lut_site<S_T, NLUT>(j)) {
-      v = lds_f32(r[col - C0 + SHIFT]);
+      v = (NEMB200_EXP & 1) ? __uint_as_float(r[col - C0 + SHIFT]) : lds_f32(r[col - C0 + SHIFT]);
     } else {
       // (re)load the float4 of biases that holds site j (ex2 groups start on a 16-byte boundary)
       if ((j & 3) == 0 || col == C0) b4 = *reinterpret_cast<const float4 *>(sBias + g * kBiasStride + (j & ~3));
       const int w = j & 3;
       const float b = w == 0 ? b4.x : (w == 1 ? b4.y : (w == 2 ? b4.z : b4.w));
-      v = ex2f(fmaf((float)(int)r[col - C0 + SHIFT], p.k1, b));
+      v = ex2f(fmaf(__uint_as_float((r[col - C0 + SHIFT] << 9) + kMagic14), p.k1, b));
     }
     if (j == 8 || (S_T <= 8 && j == S_T - 1)) finalize_pending(pd, p, part);  // previous graph, mid-stream
     acc[j & 3] += v;
@@ -488,6 +516,7 @@ __device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem
   constexpr int G = tile_graphs(S_T);
   constexpr int NCOL = (G / epi_warpgroups(S_T)) * S_T;  // this warpgroup's share of the tile's graphs
   constexpr int NA = NCOL < 32 ? NCOL : 32, NB = NCOL - NA;
+  constexpr int NA1 = NB > 0 ? (NA < 12 ? NA : 12) : 0;  // look-ups of chunk A done before the early hand-back of the buffer
   static_assert(NCOL <= 64, "a warpgroup's share must fit two 32-column TMEM loads");
   // The second load is 8, 16 or 32 columns wide and ENDS at the warpgroup's last column (it never reads past
   // the warpgroup's share, so the last warpgroup stays inside the 256-column buffer); its first BSH registers
@@ -520,24 +549,26 @@ __device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem
     ETRACE(0);
     tmem_wait_ld();  // A(t) is in registers
     ETRACE(1);
-    if (NB > 0) TMEM_LDN(NB, tmem_cols + buf * 256u + (uint32_t)BSTART, rb);
-    static_cols<S_T, NLUT, 0, NA>(ra, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
+    if (NB > 0 && (!(NEMB200_EXP & 2) || t == 0)) TMEM_LDN(NB, tmem_cols + buf * 256u + (uint32_t)BSTART, rb);
+    // The accumulator buffer goes back to the MMA issuer as soon as chunk B(t) has landed in registers, which is a
+    // few look-ups into chunk A (the load was issued just above): the MMA of tile t+2 then has most of a tile
+    // period to complete, and nothing this warp waits for later in the tile depends on the other 15 warps.
+    static_cols<S_T, NLUT, 0, NA1>(ra, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
     ETRACE(2);
-    const uint32_t itn = it0 + (uint32_t)t + 1u, nbuf = itn & 1u;
-    uint32_t ready = 0;
-    if (t + 1 < nt) ready = mbar_test(bar_tfull + 8 * nbuf, (itn >> 1) & 1u);  // probe early, consume after the release
     if (NB > 0) tmem_wait_ld();  // B(t) is in registers: this warp no longer needs the accumulator buffer
     ETRACE(3);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     ETRACE(4);
+    static_cols<S_T, NLUT, NA1, NA, NA1>(ra, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
+    const uint32_t itn = it0 + (uint32_t)t + 1u, nbuf = itn & 1u;
     if (t + 1 < nt) {
       buf = nbuf;
-      if (!ready) mbar_wait(bar_tfull + 8 * buf, (itn >> 1) & 1u);
+      mbar_wait(bar_tfull + 8 * buf, (itn >> 1) & 1u);  // (complete long ago in steady state: ~90 clk)
       ETRACE(5);
       tc_fence_after();
-      TMEM_LDN(NA, tmem_cols + buf * 256u, ra);
+      if (!(NEMB200_EXP & 2)) TMEM_LDN(NA, tmem_cols + buf * 256u, ra);  // lands while chunk B is being looked up
     }
     ETRACE(6);
     if (NB > 0) static_cols<S_T, NLUT, NA, NCOL, BSH>(rb, sBias, p, valid, ng_mine, acc, b4, null_term, pd, part);
@@ -545,6 +576,140 @@ __device__ __forceinline__ void item_tiles_static(const Params &p, uint32_t tmem
   }
   finalize_pending(pd, p, part);
 #undef ETRACE
+}
+
+// ---- lean table epilogue (every site through the table): the kernel is bound by the instructions its 16 epilogue
+// warps issue (4 warps per scheduler, each in order), so this path counts them: look-ups are consumed in PAIRS by one
+// packed FADD2 (add.f32x2), the tile loop is unrolled over the two accumulator buffers so that every barrier address
+// and TMEM column is an immediate, the per-graph logarithm is branch-free (FSEL instead of a divergent block) and
+// takes the float exponent by a magic-number add instead of I2F.  Per (warp, tile): S_T LDS + S_T/2 FADD2 + ~35.
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+struct LeanPending { float sum; int g; bool ok; };
+// log2 of a positive normal float + cexp (the scale): biased exponent taken as 2^23 + e by one shift-add (no I2F),
+// mantissa through lg2.approx
+__device__ __forceinline__ void lean_finalize(LeanPending &pd, float cexp, double (&part)[kMaxG / 4]) {
+  if ((NEMB200_EXP & 4) && pd.sum != 123.f) return;
+  const uint32_t b = __float_as_uint(pd.sum);
+  const float ef = __uint_as_float((b >> 23) + 0x4B000000u);  // 2^23 + biased exponent, exact
+  float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u), l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(m));
+  // same roundings as log2_split(x) + scale (the fused MCMC kernel computes exactly that: both order-MCMC paths
+  // then take bit-identical accept decisions): (e + lg2 m) + scale, with e = ef - (2^23 + 127) exact
+  l = ((ef - 8388735.f) + l) + cexp;
+  l = pd.ok ? l : 0.f;
+#pragma unroll
+  for (int g = 0; g < kMaxG / 4; ++g)
+    if (g == pd.g) part[g] += (double)l;                     // pd.g is a compile-time constant at every call site
+}
+
+// all look-ups of the chunk are ISSUED before the first one is consumed: the kernel lives on the number of shared-memory
+// loads in flight (16 in-order warps; ptxas on its own batches them in eights, which caps the LSU at ~0.6 loads/clk)
+template <int N>
+__device__ __forceinline__ void pin_regs(float (&v)[N]) {
+  if constexpr (N >= 16) {
+    float(&a)[16] = reinterpret_cast<float(&)[16]>(v[0]);
+    asm volatile("" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]),
+                      "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]));
+    if constexpr (N > 16) pin_regs<N - 16>(reinterpret_cast<float(&)[N - 16]>(v[16]));
+  } else if constexpr (N >= 4) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]));
+    if constexpr (N > 4) pin_regs<N - 4>(reinterpret_cast<float(&)[N - 4]>(v[4]));
+  } else if constexpr (N >= 2) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]));
+  }
+}
+
+template <int S_T, int C0, int C1, int SHIFT>
+__device__ __forceinline__ void lean_cols(const uint32_t (&r)[32], float null_term, float cexp, bool ok_tile, int ng_mine,
+                                          uint64_t &a0, uint64_t &a1, LeanPending &pd, double (&part)[kMaxG / 4]) {
+  static_assert(S_T % 2 == 0 && C0 % 2 == 0 && C1 % 2 == 0, "column pairs must not straddle graphs or chunks");
+  if constexpr (C1 > C0) {
+    float v[C1 - C0];
+#pragma unroll
+    for (int i = 0; i < C1 - C0; ++i) v[i] = (NEMB200_EXP & 1) ? __uint_as_float((r[i + SHIFT] & 0xFFFFu) | 0x3F800000u) : lds_f32(r[i + SHIFT]);
+#if NEMB200_LDS_BATCH
+    pin_regs<C1 - C0>(v);
+#endif
+#pragma unroll
+    for (int col = C0; col < C1; col += 2) {
+      const int g = col / S_T, j = col % S_T;
+      if (j == 0) { a0 = pack2(null_term, 0.f); a1 = pack2(0.f, 0.f); }
+      const uint64_t v2 = pack2(v[col - C0], v[col + 1 - C0]);
+      if (j == (S_T > 8 ? 8 : S_T - 2)) lean_finalize(pd, cexp, part);  // the previous graph's logarithm, mid-stream
+      if (j & 2) a1 = add2(a1, v2); else a0 = add2(a0, v2);
+      if (j == S_T - 2) {
+        float x0, y0, x1, y1;  // (acc0 + acc1) + (acc2 + acc3): the association of every other epilogue of this file
+        unpack2(a0, x0, y0); unpack2(a1, x1, y1);
+        pd.sum = (x0 + y0) + (x1 + y1); pd.g = g; pd.ok = ok_tile && g < ng_mine;
+      }
+    }
+  }
+}
+
+template <int S_T>
+__device__ __forceinline__ void item_tiles_lean(const Params &p, uint32_t tmem_cols, int ng_mine, int row0, int nt, uint32_t it0,
+                                                uint32_t bar_tfull, uint32_t bar_tempty, double (&part)[kMaxG / 4]) {
+  constexpr int G = tile_graphs(S_T);
+  constexpr int NCOL = (G / epi_warpgroups(S_T)) * S_T;
+  // chunk A = columns [0, NA), chunk B = [NA, NCOL): two TMEM loads of up to 32 columns per tile, each issued one
+  // chunk of look-ups before it is needed (NEMB200_CA: columns of chunk A when the share is wider than 32)
+  constexpr int NA = NCOL <= 32 ? NCOL : ((NEMB200_CA >= NCOL - 32 && NEMB200_CA <= 32) ? NEMB200_CA : 32), NB = NCOL - NA;
+  constexpr int NA1 = NB > 0 ? (NA < NEMB200_NA1 ? NA : NEMB200_NA1) : 0;  // look-ups of chunk A before the accumulator buffer is handed back
+  static_assert(NCOL <= 64 && NA <= 32 && NB <= 32 && NA % 2 == 0, "a warpgroup's share must fit two 32-column TMEM loads");
+  constexpr int NAL = NA > 16 ? 32 : (NA > 8 ? 16 : 8);
+  constexpr int NBL = NB > 16 ? 32 : (NB > 8 ? 16 : 8);
+  constexpr int BSTART = NB > 0 ? NCOL - NBL : 0, BSH = NB > 0 ? NA - BSTART : 0;
+  const int lane = threadIdx.x & 31;
+  const float null_term = ex2f(-p.scale), cexp = p.scale;
+  // opaque copies: ptxas otherwise rematerialises the shared-window base (S2R + LEA) in front of every barrier op
+  uint32_t bfull = bar_tfull, bempty = bar_tempty, tcols = tmem_cols;
+  asm volatile("" : "+r"(bfull), "+r"(bempty), "+r"(tcols));
+  uint32_t ra[32], rb[32];
+  uint64_t a0 = 0, a1 = 0;
+  LeanPending pd = {1.f, 0, false};
+  uint32_t ph = (it0 >> 1) & 1u;  // parity of the t_full barriers for the current PAIR of tiles
+  // one tile out of accumulator buffer BUF; `more`: another tile follows (its chunk A is fetched before chunk B is used)
+  auto tile = [&](auto buf_c, int t, bool more) {
+    constexpr uint32_t BUF = decltype(buf_c)::value;
+    const bool ok_tile = row0 + t * 128 < p.E;
+    tmem_wait_ld();  // A(t) is in registers
+    if constexpr (NB > 0) { if (!(NEMB200_EXP & 2)) TMEM_LDN(NB, tcols + BUF * 256u + (uint32_t)BSTART, rb); }
+    lean_cols<S_T, 0, NA1, 0>(ra, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
+    if constexpr (NB > 0) tmem_wait_ld();  // B(t) is in registers: this warp no longer needs the accumulator buffer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bempty + 8 * BUF);
+    lean_cols<S_T, NA1, NA, NA1>(ra, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
+    if (more) {
+      mbar_wait(bfull + 8 * (BUF ^ 1u), BUF ? (ph ^ 1u) : ph);
+      tc_fence_after();
+      if (!(NEMB200_EXP & 2)) TMEM_LDN(NAL, tcols + (BUF ^ 1u) * 256u, ra);  // lands while chunk B is being looked up
+    }
+    if constexpr (NB > 0) lean_cols<S_T, NA, NCOL, BSH>(rb, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
+  };
+  int t = 0;
+  if (it0 & 1u) {  // the item starts on buffer 1
+    mbar_wait(bfull + 8, ph);
+    tc_fence_after();
+    TMEM_LDN(NAL, tcols + 256u, ra);
+    tile(std::integral_constant<uint32_t, 1>{}, 0, nt > 1);
+    ph ^= 1u;
+    t = 1;
+  } else {
+    mbar_wait(bfull, ph);
+    tc_fence_after();
+    TMEM_LDN(NAL, tcols, ra);
+  }
+  for (; t + 1 < nt; t += 2) {
+    tile(std::integral_constant<uint32_t, 0>{}, t, true);
+    tile(std::integral_constant<uint32_t, 1>{}, t + 1, t + 2 < nt);
+    ph ^= 1u;
+  }
+  if (t < nt) tile(std::integral_constant<uint32_t, 0>{}, t, false);
+  lean_finalize(pd, cexp, part);
 }
 
 template <int EPI, int S_T, int NLUT, bool PAIR = false>
@@ -666,7 +831,9 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
         brow[sw128((uint32_t)col, (uint32_t)(S + 1))] = (uint8_t)(q - b0);
         brow[sw128((uint32_t)col, (uint32_t)(S + 2))] = (uint8_t)((addr & 127u) >> 2);
       } else {
-        if (gi < G && j < kBiasStride * 2) bias[gi * bstride + j] = p.kc * (float)cnt - p.scale;
+        // (specialised mixed kernels convert the accumulator with the 2^14 magic number, see kMagic14)
+        if (gi < G && j < kBiasStride * 2)
+          bias[gi * bstride + j] = p.kc * (float)cnt - p.scale - ((S_T > 0 && NLUT < S_T) ? p.k1 * 16384.f : 0.f);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -688,49 +855,57 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
 
   if (warp == 0) {
     // =============================== TMA producer: A tiles of every item, in order ===================
-    if (lane == 0) {
-      uint32_t it = 0;
-      Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
-      Item im;
-      while (wk.next(im, p.n_mtiles)) {
-        const int m0 = im.m0, nt = im.nt;
-        for (int t = 0; t < nt; ++t, ++it) {
-          const uint32_t st = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(bar_aempty + 8 * st, ph ^ 1u);
-          TRACE(0, it, 0);
-          if (DBG(4)) { mbar_arrive(bar_afull + 8 * st); continue; }
-          const uint32_t tma_bytes = DBG(16) ? kTileBytes / 2 : kTileBytes;  // diagnostics: half the operand traffic (wrong results)
-          mbar_expect_tx(bar_afull + 8 * st, tma_bytes);
-          bulk_g2s(sbase + L::A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, tma_bytes, bar_afull + 8 * st);
+    // The whole warp walks the loop (uniform control flow: addresses and barrier parities stay in uniform
+    // registers) and ONE elected lane issues; a loop under `if (lane == 0)` makes ptxas wrap every bulk copy / MMA
+    // in an ELECT + R2UR.BROADCAST retry loop (five register moves per instruction through the vector pipe).
+    uint32_t it = 0;
+    Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
+    Item im;
+    while (wk.next(im, p.n_mtiles)) {
+      const int m0 = im.m0, nt = im.nt;
+      for (int t = 0; t < nt; ++t, ++it) {
+        const uint32_t st = it % kStages, ph = (it / kStages) & 1u;
+        mbar_wait(bar_aempty + 8 * st, ph ^ 1u);
+        TRACE(0, it, 0);
+        if (elect_one()) {
+          if (DBG(4) || (NEMB200_EXP & 16)) {
+            mbar_arrive(bar_afull + 8 * st);
+          } else {
+            const uint32_t tma_bytes = DBG(16) ? kTileBytes / 2 : kTileBytes;  // diagnostics: half the operand traffic (wrong results)
+            mbar_expect_tx(bar_afull + 8 * st, tma_bytes);
+            bulk_g2s(sbase + L::A + st * kTileBytes, p.a_img + (size_t)(m0 + t) * kTileBytes, tma_bytes, bar_afull + 8 * st);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer =======================================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
-      Item im;
-      for (int k = 0; wk.next(im, p.n_mtiles); ++k) {
-        const int nt = im.nt;
-        const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
-        mbar_wait(bar_bfull + 8 * bb, bbph);  // this item's B operand is expanded
-        const uint32_t b0 = sbase + L::B + bb * 2 * kTileBytes;
-        for (int t = 0; t < nt; ++t, ++it) {
-          const uint32_t st = it % kStages, ph = (it / kStages) & 1u, buf = it & 1u, bph = (it >> 1) & 1u;
-          TRACE(1, it, 0);
-          mbar_wait(bar_afull + 8 * st, ph);
-          TRACE(1, it, 1);
-          mbar_wait(bar_tempty + 8 * buf, bph ^ 1u);
-          TRACE(1, it, 2);
-          tc_fence_after();
-          const uint32_t a0 = sbase + L::A + st * kTileBytes;
-          for (int ks = 0; ks < (DBG(2) ? 0 : p.ksteps); ++ks)
+    // =============================== MMA issuer (warp-uniform loop, one elected lane issues) ==========
+    uint32_t it = 0;
+    Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
+    Item im;
+    for (int k = 0; wk.next(im, p.n_mtiles); ++k) {
+      const int nt = im.nt;
+      const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
+      mbar_wait(bar_bfull + 8 * bb, bbph);  // this item's B operand is expanded
+      const uint32_t b0 = sbase + L::B + bb * 2 * kTileBytes;
+      for (int t = 0; t < nt; ++t, ++it) {
+        const uint32_t st = it % kStages, ph = (it / kStages) & 1u, buf = it & 1u, bph = (it >> 1) & 1u;
+        TRACE(1, it, 0);
+        mbar_wait(bar_afull + 8 * st, ph);
+        TRACE(1, it, 1);
+        mbar_wait(bar_tempty + 8 * buf, bph ^ 1u);
+        TRACE(1, it, 2);
+        tc_fence_after();
+        const uint32_t a0 = sbase + L::A + st * kTileBytes;
+        if (elect_one()) {
+          for (int ks = 0; ks < (DBG(2) ? 0 : ((NEMB200_EXP & 32) ? 1 : ((NEMB200_EXP & 64) ? 0 : p.ksteps))); ++ks)
             umma_i8(tmem_base + buf * 256u, umma_desc(a0 + ks * 32), umma_desc(b0 + ks * 32), idesc, ks > 0 ? 1u : 0u);
           umma_commit(bar_aempty + 8 * st);  // A slot reusable once these MMAs retire
           umma_commit(bar_tfull + 8 * buf);  // accumulator ready for the epilogue
-          TRACE(1, it, 3);
         }
+        __syncwarp();
+        TRACE(1, it, 3);
       }
     }
   } else if (warp < 4) {
@@ -828,7 +1003,10 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
 #pragma unroll
       for (int g = 0; g < kMaxG / 4; ++g) part[g] = 0.0;
       if (S_T > 0 && ng_mine > 0) {
-        if constexpr (S_T > 0)
+        if constexpr (S_T > 0 && NLUT >= S_T && S_T % 2 == 0 && !NEMB200_OLD_EPILOGUE)
+          item_tiles_lean<S_T>(p, tmem_base + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16), ng_mine,
+                               m0 * 128 + quarter * 32 + lane, nt, it, bar_tfull, bar_tempty, part);
+        else if constexpr (S_T > 0)
           item_tiles_static<S_T, NLUT>(p, tmem_base + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16), bias, ng_mine,
                                        m0 * 128 + quarter * 32 + lane, nt, it, bar_tfull, bar_tempty, part);
         it += (uint32_t)nt;
@@ -1146,10 +1324,21 @@ int launch_kernel(K kern, const Params &p, int grid, int threads, cudaStream_t s
 int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t st) {
   // the dataset fixed the column stride: S itself for the four headline shapes, S rounded up to 8 otherwise
   switch (h->CS == h->S ? h->S : -h->CS) {
+#ifndef NEMB200_DEV_S50  // (development builds compile the S=50 instantiations only)
     case 10: return launch_kernel(k_score_tc<EPI_LUT, 10, 10>, p, grid, cta_threads(10), st);
     case 20: return launch_kernel(k_score_tc<EPI_LUT, 20, 20>, p, grid, cta_threads(20), st);
     case 30: return launch_kernel(k_score_tc<EPI_LUT, 30, 30>, p, grid, cta_threads(30), st);
-    case 50: return launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, cta_threads(50), st);
+#endif
+    case 50: {
+      static const char *mix_env = getenv("NEMB200_MIX");  // diagnostics: 1/P of the sites through ex2.approx
+      const int mix = mix_env ? atoi(mix_env) : 0;
+      if (mix == 3) return launch_kernel(k_score_tc<EPI_LUT, 50, 3>, p, grid, cta_threads(50), st);
+      if (mix == 4) return launch_kernel(k_score_tc<EPI_LUT, 50, 4>, p, grid, cta_threads(50), st);
+      if (mix == 5) return launch_kernel(k_score_tc<EPI_LUT, 50, 5>, p, grid, cta_threads(50), st);
+      if (mix == 6) return launch_kernel(k_score_tc<EPI_LUT, 50, 6>, p, grid, cta_threads(50), st);
+      return launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, cta_threads(50), st);
+    }
+#ifndef NEMB200_DEV_S50
     case 8: case -8: return launch_kernel(k_score_tc<EPI_LUT, 8, 8>, p, grid, cta_threads(8), st);
     case 16: case -16: return launch_kernel(k_score_tc<EPI_LUT, 16, 16>, p, grid, cta_threads(16), st);
     case 24: case -24: return launch_kernel(k_score_tc<EPI_LUT, 24, 24>, p, grid, cta_threads(24), st);
@@ -1158,6 +1347,7 @@ int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t
     case 48: case -48: return launch_kernel(k_score_tc<EPI_LUT, 48, 48>, p, grid, cta_threads(48), st);
     case 56: case -56: return launch_kernel(k_score_tc<EPI_LUT, 56, 56>, p, grid, cta_threads(56), st);
     case -64: return launch_kernel(k_score_tc<EPI_LUT, 64, 64>, p, grid, cta_threads(64), st);
+#endif
     default: return launch_kernel(k_score_tc<EPI_LUT, 0, 0>, p, grid, cta_threads(0), st);
   }
 }
@@ -1237,10 +1427,14 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   if (!pair && n <= 2048 && leave_sms_free == 0) {
     // one self-resetting completion counter per distinct workspace (launches that share a workspace are ordered by
     // the caller anyway); when the pool is exhausted the separate finalize kernel is used
-    nemb200_dataset *hm = const_cast<nemb200_dataset *>(h);
+    // (the counters themselves sit in the dataset workspace, which the library zeroed: caller memory is not zero at rest)
+    nemb200_cache *hm = h->cache;
     int slot = -1;
-    for (int i = 0; i < hm->n_ctr; ++i) if (hm->ctr_ws[i] == ws) { slot = i; break; }
-    if (slot < 0 && hm->n_ctr < 64) { slot = hm->n_ctr++; hm->ctr_ws[slot] = ws; }
+    {
+      std::lock_guard<std::recursive_mutex> lock(hm->mu);
+      for (int i = 0; i < hm->n_ctr; ++i) if (hm->ctr_ws[i] == ws) { slot = i; break; }
+      if (slot < 0 && hm->n_ctr < 64) { slot = hm->n_ctr++; hm->ctr_ws[slot] = ws; }
+    }
     if (slot >= 0) p.done_counter = h->counters + slot;
   }
   const int grid = effective_ctas(T, h->n_mtiles, nsm);

@@ -340,7 +340,7 @@ class ChainState:
         n, S = o.shape
         if S != ds.S:
             raise ValueError(f"orders have {S} entries, dataset has S={ds.S}")
-        if not all(np.array_equal(np.sort(r), np.arange(S)) for r in o[: min(n, 64)]):
+        if not (np.sort(o, axis=1) == np.arange(S, dtype=np.int32)).all():   # every row: the kernels index by label
             raise ValueError("each start order must be a permutation of range(S)")
         self.n, self.S, self.W = n, S, ds.W
         self.orders = torch.from_numpy(o).to(dev)
@@ -391,16 +391,34 @@ class ChainState:
         self.trace = tr
         return self
 
-    def replica_exchange(self, ladder: int, phase: int, round_idx: int) -> torch.Tensor:
-        """Neighbour swaps inside ladders of `ladder` consecutive chains (nem_order_mcmc.py:326-340)."""
+    def replica_exchange(self, ladder: int, phase: int, round_idx: int, faithful: bool = False) -> torch.Tensor:
+        """Neighbour swaps inside ladders of `ladder` consecutive chains (nem_order_mcmc.py:326-340).
+        Default: delta (:333) from the chains' current scores (standard parallel tempering).  faithful=True: the
+        reference's own criterion - scores[i] = replicas[i].best_score (:321), whole replicas (current AND best
+        state) change places (:335); use `restart_best()` before each round to get method()'s per-call best (:259-260)."""
         ds = self.ds
         nsw = torch.zeros(1, dtype=torch.int64, device=ds.device)
         st = torch.cuda.current_stream(ds.device)
-        _lib.check(_lib.lib().nemb200_replica_exchange(self.n, int(ladder), int(phase), int(round_idx),
-                                                       C.c_uint64(self.seed), self.S, _ptr(self.gamma),
-                                                       _ptr(self.orders), _ptr(self.curr_scores), _ptr(self.curr_bits),
-                                                       _ptr(nsw), _stream_ptr(st)))
+        L = _lib.lib()
+        if faithful:
+            _lib.check(L.nemb200_replica_exchange_best(self.n, int(ladder), int(phase), int(round_idx), C.c_uint64(self.seed),
+                                                       self.S, _ptr(self.gamma), _ptr(self.orders), _ptr(self.curr_scores),
+                                                       _ptr(self.curr_bits), _ptr(self.best_scores), _ptr(self.best_orders),
+                                                       _ptr(self.best_bits), _ptr(nsw), _stream_ptr(st)))
+        else:
+            _lib.check(L.nemb200_replica_exchange(self.n, int(ladder), int(phase), int(round_idx), C.c_uint64(self.seed),
+                                                  self.S, _ptr(self.gamma), _ptr(self.orders), _ptr(self.curr_scores),
+                                                  _ptr(self.curr_bits), _ptr(nsw), _stream_ptr(st)))
         return nsw
+
+    def restart_best(self):
+        """method() starts every call with best_score = curr_score, best_dag / best_order = the current ones
+        (nem_order_mcmc.py:259-265): device copies, no host sync.  The first run() must have scored the start orders."""
+        if not self.started:
+            self.run(0)
+        self.best_scores.copy_(self.curr_scores)
+        self.best_orders.copy_(self.orders)
+        self.best_bits.copy_(self.curr_bits)
 
     def edge_count_matrix(self) -> torch.Tensor:
         """int64 (S,S) device tensor: per-chain posterior edge counts summed over this GPU's chains."""

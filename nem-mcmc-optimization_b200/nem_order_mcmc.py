@@ -291,10 +291,16 @@ class NEMOrderMCMC:
 
 
 def replica_exchange_method(nem, n_exchange, n_iter, init_order_guess, n_replicas=10, seed=1234, rule="full",
-                            cand=None, use_nem=False, swap_prob=0.95, n_ladders=1):
+                            cand=None, use_nem=False, swap_prob=0.95, n_ladders=1, faithful=False):
     """nem_order_mcmc.py:344-363: `n_replicas` tempered chains at gamma_r = (1 + 0.2 r) S/E (:351), each
     exchange round runs n_iter iterations on every replica (device, concurrently) and then swaps even/odd
-    neighbours with probability exp(-delta) (:326-340).  Returns (best_score, best replica)."""
+    neighbours with probability exp(-delta) (:326-340).  Returns (best_score, best replica).
+
+    faithful=False (default): delta (:333) uses the replicas' CURRENT scores - standard parallel tempering, detailed
+    balance holds.  faithful=True: what replica_exchange_step literally does - every round restarts each replica's
+    best_score from its current score (method(), :259-260), delta uses scores[i] = replicas[i].best_score (:321),
+    whole replicas change places (:335-336), and the overall best (best_score, best_nem) is the best over rounds
+    (:322-324, :338-340); the test-suite checks this mode swap for swap against a statement-for-statement restatement."""
     S, E = nem.num_s, nem.num_e
     n = n_replicas * n_ladders
     gammas = np.tile((1.0 + 0.2 * np.arange(n_replicas)) * S / E, n_ladders)
@@ -303,12 +309,25 @@ def replica_exchange_method(nem, n_exchange, n_iter, init_order_guess, n_replica
     state = engine.ChainState(getattr(nem, "score_dataset", nem.dataset), orders0, gammas, edge_counts=False, seed=seed, rule=_RULES[rule], cand=cand,
                               use_nem=use_nem)
     n_swaps = 0
+    overall = None  # faithful mode: (best_score, order, graph) over all rounds
     for r in range(n_exchange):
+        if faithful:
+            state.restart_best()
         state.run(n_iter, swap_prob=swap_prob)
-        n_swaps += int(state.replica_exchange(n_replicas, r & 1, r).item())
+        if faithful:
+            bs = state.best_scores.cpu().numpy()
+            k = int(np.argmax(bs))                                  # :322-324
+            if overall is None or bs[k] > overall[0]:
+                overall = (float(bs[k]), state.best_orders[k].cpu().numpy().copy(),
+                           engine.unpack_adj(state.best_bits[k:k + 1].cpu().numpy().view(np.uint32), S)[0])
+        n_swaps += int(state.replica_exchange(n_replicas, r & 1, r, faithful=faithful).item())
     res = state.result()
-    k = int(np.argmax(res.best_scores))
-    best = NEMOrderMCMC(nem, res.best_orders[k])
-    best.best_score, best.best_dag, best.best_order = float(res.best_scores[k]), res.best_graphs[k].astype(int), res.best_orders[k]
+    if faithful and overall is not None:
+        score, order, graph = overall
+    else:
+        k = int(np.argmax(res.best_scores))
+        score, order, graph = float(res.best_scores[k]), res.best_orders[k], res.best_graphs[k]
+    best = NEMOrderMCMC(nem, order)
+    best.best_score, best.best_dag, best.best_order = score, graph.astype(int), order
     best.n_exchanges, best.state = n_swaps, state
     return best.best_score, best

@@ -118,6 +118,35 @@ def read_csv_to_adj(pathname):
     return adj, end_nodes, errors, num_s, num_e
 
 
+def write_network_csv(adj, end_nodes, errors, output_file, output_file_red=None):
+    """Writes a network in the reference's CSV format (DAGs/rnd_dag_gen.py:86-103, read back by
+    utils.read_csv_to_adj :96-118): line 1 ``S,E``; one ``i,j`` line per edge i -> j; one line of E attachment
+    indices; last line ``alpha,beta``; csv.writer's CRLF line ends like the shipped files.  `output_file` receives
+    the transitive closure of `adj` (networkN.csv), `output_file_red` - if given - its transitive reduction
+    (networkN_red.csv); both are computed on the GPU (closure / transitive_reduction of this module).  Edges are
+    written in row-major order (the reference writes them in generation order, which its reader ignores)."""
+    import csv
+    adj = np.asarray(adj)
+    S = adj.shape[0]
+    closed = ancestor(adj)
+    first = [S, len(end_nodes)]
+    ends = [int(x) for x in end_nodes]
+    probs = [float(x) for x in errors]
+
+    def dump(path, mat):
+        with open(path, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(first)
+            w.writerows((int(i), int(j)) for i, j in zip(*np.nonzero(mat)))
+            w.writerow(ends)
+            w.writerow(probs)
+
+    dump(output_file, closed)
+    if output_file_red is not None:
+        dump(output_file_red, transitive_reduction(closed))
+    return closed
+
+
 def transitive_reduction(adj_matrix):
     """utils.py:120-129 (result post-processing), on the GPU (`nemb200_transitive_reduction_u32`): the
     reference's in-place triple loop, reproduced exactly - the Hasse diagram for a closed DAG; nonzero entries count
@@ -128,8 +157,9 @@ def transitive_reduction(adj_matrix):
 
 
 def hamming_distance(mat_a, mat_b):
-    """utils.py:148-149."""
-    return np.sum(np.abs(np.asarray(mat_a) - np.asarray(mat_b)))
+    """utils.py:148-149 (sum |a - b|).  The reference always has int matrices here; this package hands out uint8
+    graphs (closure, transitive_reduction, best_graphs), whose difference would wrap - subtract in int64."""
+    return np.sum(np.abs(np.asarray(mat_a).astype(np.int64) - np.asarray(mat_b).astype(np.int64)))
 
 
 

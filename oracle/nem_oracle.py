@@ -298,7 +298,7 @@ def swap_prob_to_u32(p):
 
 
 def mcmc_chain(D, A, B, order0, n_iter, gamma, swap_prob=0.95, seed=1234, chain=0,
-               rule=RULE_FULL, cand=None, use_nem=True, score_fn=None, burn_in=0):
+               rule=RULE_FULL, cand=None, use_nem=True, score_fn=None, burn_in=0, iter0=0):
     """Restatement of NEMOrderMCMC.method's loop, nem_order_mcmc.py:272-302, with the clean
     (no-expit) score nem.py:72-86 and a deterministic order->DAG rule.
 
@@ -319,7 +319,7 @@ def mcmc_chain(D, A, B, order0, n_iter, gamma, swap_prob=0.95, seed=1234, chain=
     all_scores, curr_scores = [curr], [curr]
     n_acc = 0
     edge_counts = np.zeros((s, s), dtype=np.int64)
-    for t in range(n_iter):
+    for t in range(iter0, iter0 + n_iter):   # iter0: the run continues a chain that has done iter0 iterations
         r = philox4x32_10(t & _M32, (t >> 32) & _M32, chain & _M32, 0, k0, k1)
         cand_order = propose(curr_order, r, sp)
         g = order_to_graph(cand_order, rule, cand, use_nem)
@@ -339,6 +339,79 @@ def mcmc_chain(D, A, B, order0, n_iter, gamma, swap_prob=0.95, seed=1234, chain=
     return dict(best_score=best, best_order=best_order, best_graph=best_g, curr_score=curr,
                 curr_order=curr_order, n_accept=n_acc, all_score_list=all_scores,
                 curr_score_list=curr_scores, edge_counts=edge_counts)
+
+
+# --------------------------------------------------------------------------
+# replica exchange (nem_order_mcmc.py:316-363)
+# --------------------------------------------------------------------------
+
+
+def replica_exchange_step(replicas, gammas, n_replicas, scores, upwards_cycle, round_idx, seed, ladder_id=0,
+                          use_best=True):
+    """nem_order_mcmc.py:316-342 after the replicas' method() calls (:318-321), statement for statement.
+
+    `replicas` is a list of dicts as returned by mcmc_chain (one round of n_iters iterations each).
+    scores[i] = replicas[i]["best_score"] (:321; use_best=False takes "curr_score" instead - the
+    standard parallel-tempering criterion the CUDA path offers as its default).  best_nem = the replica with the
+    largest score (:322-324).  Partners (:326-331): upwards cycle (0,1),(2,3),.., else (1,2),(3,4),..
+    delta as :333; swap iff u < exp(-delta) (:334) exchanges the replica objects and their scores (:335-336);
+    the re-check of best_score (:338-340) is kept although the swap cannot change the maximum.
+    The reference draws u from the process-global Mersenne Twister (`random.random()`); here, as on
+    the device, pair k of the ladder takes u = (r3 + 0.5) / 2^32 of Philox(counter = (round lo, round hi,
+    ladder_id * (n_replicas // 2) + k, 1), key = seed).
+    Returns (best_score, best_nem, replicas, scores, n_exchanges) like the reference."""
+    n_exchanges = 0
+    for i in range(n_replicas):
+        scores[i] = replicas[i]["best_score" if use_best else "curr_score"]       # :321
+    best_score = np.max(scores)                                                   # :322
+    best_nem = replicas[int(np.argmax(scores))]                                   # :324
+    if upwards_cycle:
+        partners = [(j - 1, j) for j in range(1, n_replicas, 2)]                  # :328
+    else:
+        partners = [(j - 1, j) for j in range(2, n_replicas, 2)]                  # :331
+    k0, k1 = seed & _M32, (seed >> 32) & _M32
+    for k, (i, j) in enumerate(partners):
+        delta = gammas[i] * scores[j] - gammas[i] * scores[i] + gammas[j] * scores[i] - gammas[j] * scores[j]   # :333
+        pid = ladder_id * (n_replicas // 2) + k
+        r = philox4x32_10(round_idx & _M32, (round_idx >> 32) & _M32, pid & _M32, 1, k0, k1)
+        u = (r[3] + 0.5) / 4294967296.0
+        with np.errstate(over="ignore"):
+            take = u < np.exp(-delta)                                             # :334
+        if take:
+            replicas[i], replicas[j] = replicas[j], replicas[i]                   # :335
+            scores[i], scores[j] = scores[j], scores[i]                           # :336
+            n_exchanges += 1
+            if scores[i] > best_score:                                            # :338-340
+                best_score = scores[i]
+                best_nem = replicas[i]
+    return best_score, best_nem, replicas, scores, n_exchanges
+
+
+def replica_exchange_method(D, A, B, init_orders, n_exchange, n_iter, n_replicas=10, seed=1234, rule=RULE_FULL,
+                            cand=None, use_nem=False, swap_prob=0.95, use_best=True):
+    """nem_order_mcmc.py:344-363 around replica_exchange_step: gamma_r = (1 + 0.2 r) S / E (:351); every round each
+    replica runs n_iter iterations of the loop (mcmc_chain) FROM ITS CURRENT ORDER with the gamma of the ladder
+    position it sits at (:319), method() restarting best_score at the current score (:259-260); the cycle alternates
+    upwards / downwards (:357-359).  (At HEAD the reference cannot run this - method() raises NameError, SURVEY Q1,
+    and `perm_orders` (:320) is never defined; the restatement keeps every statement that is executable.)
+    The chain at ladder position i uses Philox chain id i and global iteration numbers r*n_iter.. like the device.
+    init_orders: (n_replicas, S).  Returns dict(best_score, best_order, best_graph, n_exchanges, replicas, trace)."""
+    s, e = np.asarray(D).shape
+    gammas = [(1.0 + i * 0.2) * s / e for i in range(n_replicas)]
+    replicas = [dict(curr_order=np.array(init_orders[i], dtype=np.int64)) for i in range(n_replicas)]
+    scores = np.zeros(n_replicas)
+    n_exchanges, overall, trace = 0, None, []
+    for r in range(n_exchange):
+        for i in range(n_replicas):                                              # :318-319
+            replicas[i] = mcmc_chain(D, A, B, replicas[i]["curr_order"], n_iter, gammas[i], swap_prob=swap_prob, seed=seed,
+                                     chain=i, rule=rule, cand=cand, use_nem=use_nem, iter0=r * n_iter)
+        best_score, best_nem, replicas, scores, ex = replica_exchange_step(replicas, gammas, n_replicas, scores, r % 2 == 0,
+                                                                            r, seed, use_best=use_best)
+        n_exchanges += ex
+        trace.append((ex, [rep["curr_order"].copy() for rep in replicas], scores.copy()))
+        if overall is None or best_score > overall["best_score"]:
+            overall = dict(best_score=best_score, best_order=best_nem["best_order"].copy(), best_graph=best_nem["best_graph"].copy())
+    return dict(overall, n_exchanges=n_exchanges, replicas=replicas, trace=trace)
 
 
 # --------------------------------------------------------------------------

@@ -200,3 +200,13 @@ def test_score_kernel_partition_invariants():
     for nt, nm, c in cases:
         assert L.nemb200_selftest_partition(nt, nm, c) == 0, (nt, nm, c)
     assert L.nemb200_selftest_partition(0, 1, 1) < 0
+
+
+def test_hamming_distance_on_uint8_graphs():
+    """the package hands out uint8 graphs; 0 - 1 must not wrap (utils.py:148-149 has int matrices)."""
+    import nem_b200
+    a = np.zeros((5, 5), dtype=np.uint8)
+    b = np.zeros((5, 5), dtype=np.uint8)
+    a[0, 1] = a[2, 3] = 1
+    b[2, 3] = b[4, 0] = b[1, 1] = 1
+    assert nem_b200.utils.hamming_distance(a, b) == 3 == nem_b200.utils.hamming_distance(b.astype(int), a.astype(int))
