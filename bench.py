@@ -265,6 +265,50 @@ def config4_shape_leg(nb, synth):
     return row
 
 
+def config4_leg(nb, synth, parallel, rank, world, dev, barrier):
+    """BASELINE config 4 as configured: S=100 x E=100 000, 4096 order-MCMC chains over the N GPUs of the box (STRONG
+    scaling: 4096/N chains per rank).  Rank 0 synthesises the data and broadcasts the bit-packed matrix once
+    (parallel.broadcast_dataset); the timed region is one run of the device-resident loop on every rank plus
+    the run's two collectives (edge-count all-reduce, best-graph broadcast); time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    s, e, n_total, iters = 100, 100000, 4096, 16
+    D0 = None
+    if rank == 0:
+        adj, _, _ = synth.dataset(s, 8, seed=0, alpha=ALPHA, beta=BETA)      # true graph only; data synthesised on the device
+        ends = np.random.default_rng(0).integers(0, s, size=e)
+        D0 = synth.device_knockdown(adj, ends, ALPHA, BETA, seed=0, device=dev)
+    A4, B4 = synth.nem_constants(ALPHA, BETA)
+    ds = parallel.broadcast_dataset(D0, A4, B4, src=0, device=dev, sort_egenes=True)
+    cand = (np.random.default_rng(7).random((s, s)) < 0.2).astype(np.uint8)
+    orders = synth.random_orders(n_total, s, seed=5)
+    lo, hi = parallel.shard_range(n_total, rank, world)
+    st = nb.ChainState(ds, orders[lo:hi], 2.0 * s / e, edge_counts=True, chain_offset=lo, seed=1234, rule=nb.RULE_MASKED,
+                       cand=cand, use_nem=True)
+    st.run(iters)                                                           # captures the loop's CUDA graph, warms NCCL
+    parallel.allreduce_edge_counts(st.edge_count_matrix())
+    parallel.global_best(st.best_scores, st.best_orders, st.best_bits, lo)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(torch.cuda.current_stream(dev))
+    st.run(iters)
+    counts = parallel.allreduce_edge_counts(st.edge_count_matrix())
+    best = parallel.global_best(st.best_scores, st.best_orders, st.best_bits, lo)
+    ev1.record(torch.cuda.current_stream(dev))
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"config": "BASELINE config 4: S=100 x E=100000, 4096 chains over the GPUs of the box", "scaling": "strong",
+            "n_gpus": world, "chains_per_gpu": hi - lo, "iters": iters, "ms_per_iteration": ms / iters,
+            "chain_iterations_per_s": n_total * iters / (ms * 1e-3),
+            "graph_scores_tflops_algorithmic": 2.0 * s * s * e * n_total * iters / (ms * 1e-3) / 1e12,
+            "collectives": "dataset broadcast once (before the run); edge-count all-reduce + best-graph broadcast inside the timed region",
+            "best_score": best[0], "edge_count_total": int(counts.sum().item()),
+            "score_impl": f"multi-level exp table ({ds.lutm_levels} levels)" if ds.lutm_levels else "ex2 two-pass"}
+
+
 def config5_sweep(nb, synth):
     """BASELINE config 5: 65 536 random DAGs, S=30 x E=5000: closure + score throughput, bit rows resident."""
     import torch
@@ -401,9 +445,10 @@ def run_gpu(args, rank, world, local_rank):
     ws, _ = ds._score_workspace(CHAINS, "pair" if 33 <= S <= 52 else "auto")  # big enough for the opt-in pair leg too
 
     def sweep(bits):
-        nb._lib.check(L.nemb200_closure_u32(C.c_void_p(bits.data_ptr()), CHAINS, S, C.c_void_p(closed.data_ptr()), sp))
-        nb._lib.check(L.nemb200_score_batch(ds._h, C.c_void_p(closed.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
-                                            C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
+        # closure + score of one batch of candidate graphs in ONE launch: the score kernel's expander warps close every
+        # graph (warp Warshall) before they build the MMA operand (nemb200_closure_score_batch)
+        nb._lib.check(L.nemb200_closure_score_batch(ds._h, C.c_void_p(bits.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
+                                                    C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -505,6 +550,10 @@ def run_gpu(args, rank, world, local_rank):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     acc_rate = float(state.accept.sum().item()) / (state.n * state.iters_done)
+    # ---- BASELINE config 4 (the multi-GPU config), every N: strong scaling of 4096 chains
+    c4 = None
+    if "config4" not in os.environ.get("BENCH_SKIP", ""):
+        c4 = config4_leg(nb, synth, parallel, rank, world, dev, barrier)
     # parity of the timed run: chain 0 of rank 0 against the C oracle's restatement of nem_order_mcmc.py:272-302 over
     # ALL iterations this state has run (same Philox stream): accept count, current order, best graph, scores
     mcmc_check = None
@@ -549,16 +598,18 @@ def run_gpu(args, rank, world, local_rank):
                                       "achieved": (S * ((E + 127) // 128 * 128) / 32.0 * CHAINS)
                                                   / (ms_kernel * 1e-3 * (sampler.summary().get("sm_mhz") or 1965.0) * 1e6 * 148)}},
             "e2e": {"value": CHAINS * world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch_bytes,
-                    "d2h_bytes_per_step": CHAINS * 8, "api": "Dataset.score_stream: closure + score_batch on pinned host bit rows, scores copied back, copies double-buffered against the kernels"},
-            # timed region of `value`: per step k_closure + k_score_tc (its finalize is fused into the last CTA for
-            # batches <= 2048 graphs, else a separate k_finalize launch)
-            "gpu_launches": (2 if CHAINS <= 2048 else 3) * K,
+                    "d2h_bytes_per_step": CHAINS * 8, "api": "Dataset.score_stream: closure + score (one fused launch per batch) on pinned host bit rows, scores copied back, copies double-buffered against the kernels"},
+            # timed region of `value`: per step ONE k_score_tc launch (closure fused into its operand expansion, finalize
+            # fused into the last CTA for batches <= 2048 graphs, else a separate k_finalize launch)
+            "gpu_launches": (1 if CHAINS <= 2048 else 2) * K,
             "mcmc": {"value": state.n * world * mc_iters / (ms_mcmc * 1e-3), "unit": "chain-iterations/s", "iters": mc_iters,
                      "chains": state.n * world, "ms_per_iter": ms_mcmc / mc_iters, "accept_rate": acc_rate,
                      "rule": "masked+closure", "collectives": "edge-count all-reduce + best-graph broadcast, once per run",
                      "best_score": best[0], "edge_count_total": int(counts.sum().item()), "oracle_check": mcmc_check},
             "clocks": sampler.summary(),
         }
+        if c4 is not None:
+            out["config4"] = c4
         if ms_pair is not None:
             out["score_pair_merged"] = {"ms_per_launch_incl_planner": ms_pair, "graph_scores_per_s": CHAINS / (ms_pair * 1e-3),
                                         "note": "impl='pair' (opt-in): k_pair_plan + pair-merged k_score_tc + fallback + finalize"}

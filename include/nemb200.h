@@ -95,6 +95,16 @@ int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_phi_bits, in
                         double *d_scores, void *d_workspace, size_t workspace_bytes, int impl,
                         void *stream);
 
+/* ---- closure + score in ONE launch: create_nem's utils.ancestor (nem_order_mcmc.py:216-221, utils.py:37-54) followed by
+ *      the score above, for candidate graphs that are not transitively closed yet (what a sweep over proposals or
+ *      `Dataset.score_graphs(close=True)` needs).  The score kernel's operand-expansion warps close each graph in
+ *      registers (the same warp Warshall as nemb200_closure_u32) before they build the MMA operand, so no closed
+ *      copy is written to HBM and no second kernel is launched.  Same workspace and `impl` rules as
+ *      nemb200_score_batch; NEMB200_SCORE_WITNESS and NEMB200_SCORE_TC_PAIR are not available here (S >= 8). */
+int nemb200_closure_score_batch(const nemb200_dataset *h, const uint32_t *d_adj_bits, int n_graphs,
+                                double *d_scores, void *d_workspace, size_t workspace_bytes, int impl,
+                                void *stream);
+
 /* ---- general-weight cell ratios: replaces compute_ll_ratios / compute_cell_ratios for real-valued
  *      parent weights (nem.py:72-80, utils.py:66-82, nem_order_mcmc.py:79-87).  d_weights: S x S
  *      float64, w[i][j] = weight of parent j for node i (0 = no edge, diagonal ignored);

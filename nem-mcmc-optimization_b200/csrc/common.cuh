@@ -94,7 +94,7 @@ int launch_score_witness(const nemb200_dataset *h, const uint32_t *phi, int n, d
                          cudaStream_t st);
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair = false);
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                    int impl, cudaStream_t st, int leave_sms_free = 0);
+                    int impl, cudaStream_t st, int leave_sms_free = 0, int close = 0);
 
 bool mcmc_fused_supported(const nemb200_dataset *h);
 bool mcmc_fused_preferred(const nemb200_dataset *h, int n_chains);

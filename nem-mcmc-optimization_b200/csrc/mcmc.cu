@@ -301,6 +301,15 @@ extern "C" int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_p
   return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream);
 }
 
+extern "C" int nemb200_closure_score_batch(const nemb200_dataset *h, const uint32_t *d_adj_bits, int n_graphs, double *d_scores,
+                                           void *d_workspace, size_t workspace_bytes, int impl, void *stream) {
+  NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
+  NEMB_REQUIRE(n_graphs == 0 || (d_adj_bits && d_scores && d_workspace), "null device pointer");
+  NEMB_REQUIRE(impl != NEMB200_SCORE_WITNESS && impl != NEMB200_SCORE_TC_PAIR && h->S >= 8,
+               "closure + score in one launch needs a tensor-core score kernel other than the pair-merged one (S >= 8)");
+  return launch_score_tc(h, d_adj_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, 1);
+}
+
 extern "C" int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_t *d_out_bits, void *stream) {
   NEMB_REQUIRE(S >= 1 && S <= NEMB200_MAX_S, "S must be in [1,%d] (got %d)", NEMB200_MAX_S, S);
   NEMB_REQUIRE(n_graphs >= 0 && (n_graphs == 0 || (d_adj_bits && d_out_bits)), "bad arguments");

@@ -99,6 +99,7 @@ struct Params {
   const double *sumN;
   double *scores;
   long long *trace;      // diagnostics only: clock64 time line of CTA 0 (NULL normally)
+  int close;             // 1: the input graphs are NOT transitively closed - the expanders close them (warp Warshall) before use
   int debug;             // diagnostics only (NEMB200_DEBUG): 1 skip epilogue math, 2 skip MMA, 4 skip TMA, 8 skip expansion
 };
 
@@ -629,10 +630,25 @@ __device__ __forceinline__ void lean_cols(const uint32_t (&r)[32], float null_te
   if constexpr (C1 > C0) {
     float v[C1 - C0];
 #pragma unroll
-    for (int i = 0; i < C1 - C0; ++i) v[i] = (NEMB200_EXP & 1) ? __uint_as_float((r[i + SHIFT] & 0xFFFFu) | 0x3F800000u) : lds_f32(r[i + SHIFT]);
+    for (int i = 0; i < C1 - C0; ++i) {
+      constexpr int kMixP = (NEMB200_EXP & 128) ? 4 : ((NEMB200_EXP & 256) ? 3 : ((NEMB200_EXP & 512) ? 2 : 0));  // timing probe: 1/P of the pairs through ex2 (wrong bias)
+      const int jj = (C0 + i) % S_T;
+      if (kMixP > 0 && ((jj >> 1) % kMixP) == kMixP - 1) v[i] = ex2f(fmaf(__uint_as_float((r[i + SHIFT] << 9) + kMagic14), -1e-4f, 1.0f));
+      else v[i] = (NEMB200_EXP & 1) ? __uint_as_float((r[i + SHIFT] & 0xFFFFu) | 0x3F800000u) : lds_f32(r[i + SHIFT]);
+    }
+    if constexpr ((NEMB200_EXP & 1024) != 0) {  // sensitivity probe: every look-up issued twice
+      float w[C1 - C0];
+#pragma unroll
+      for (int i = 0; i < C1 - C0; ++i) w[i] = lds_f32_off<4>(r[i + SHIFT]);
+      pin_regs<C1 - C0>(w);
+    }
 #if NEMB200_LDS_BATCH
     pin_regs<C1 - C0>(v);
 #endif
+    if constexpr ((NEMB200_EXP & 4096) != 0) {  // sensitivity probe: twice the packed adds
+#pragma unroll
+      for (int i = 0; i + 1 < C1 - C0; i += 2) { if (i & 2) a1 = add2(a1, pack2(v[i], v[i + 1])); else a0 = add2(a0, pack2(v[i], v[i + 1])); }
+    }
 #pragma unroll
     for (int col = C0; col < C1; col += 2) {
       const int g = col / S_T, j = col % S_T;
@@ -677,6 +693,7 @@ __device__ __forceinline__ void item_tiles_lean(const Params &p, uint32_t tmem_c
     const bool ok_tile = row0 + t * 128 < p.E;
     tmem_wait_ld();  // A(t) is in registers
     if constexpr (NB > 0) { if (!(NEMB200_EXP & 2)) TMEM_LDN(NB, tcols + BUF * 256u + (uint32_t)BSTART, rb); }
+    if constexpr (NB > 0 && (NEMB200_EXP & 2048) != 0) TMEM_LDN(NB, tcols + BUF * 256u + (uint32_t)BSTART, rb);  // sensitivity probe: twice the TMEM loads
     lean_cols<S_T, 0, NA1, 0>(ra, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
     if constexpr (NB > 0) tmem_wait_ld();  // B(t) is in registers: this warp no longer needs the accumulator buffer
     tc_fence_before();
@@ -687,6 +704,7 @@ __device__ __forceinline__ void item_tiles_lean(const Params &p, uint32_t tmem_c
       mbar_wait(bfull + 8 * (BUF ^ 1u), BUF ? (ph ^ 1u) : ph);
       tc_fence_after();
       if (!(NEMB200_EXP & 2)) TMEM_LDN(NAL, tcols + (BUF ^ 1u) * 256u, ra);  // lands while chunk B is being looked up
+      if constexpr ((NEMB200_EXP & 2048) != 0) TMEM_LDN(NAL, tcols + (BUF ^ 1u) * 256u, ra);
     }
     if constexpr (NB > 0) lean_cols<S_T, NA, NCOL, BSH>(rb, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
   };
@@ -778,6 +796,35 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       sRows[i] = p.phi[(size_t)gid * gw + (i - gi * gw)];
     }
     sync();
+    if (p.close && !((NEMB200_EXP & 8192) && nthr > 64)) {
+      // fused transitive closure (utils.ancestor, utils.py:37-54, as create_nem calls it, nem_order_mcmc.py:216-221): one
+      // warp per staged graph, rows in registers, boolean Warshall with row k broadcast by shuffle - the same
+      // warp_closure the closure kernel and the MCMC propose kernel run.  Every CTA that works on an N tile closes
+      // its own copy (a few hundred instructions per graph, hidden behind the previous item's tiles).
+      const int wi = te >> 5, nw = nthr >> 5, ln = te & 31;
+      for (int gi = wi; gi < ng; gi += nw) {
+        uint32_t *rows = sRows + gi * gw;
+        auto run = [&](auto tw_c) {
+          constexpr int TW = decltype(tw_c)::value;
+          uint32_t r[TW][TW];
+#pragma unroll
+          for (int t = 0; t < TW; ++t)
+#pragma unroll
+            for (int w = 0; w < TW; ++w) r[t][w] = (t * 32 + ln < S) ? rows[(t * 32 + ln) * TW + w] : 0u;
+          warp_closure<TW>(r, S);
+#pragma unroll
+          for (int t = 0; t < TW; ++t)
+#pragma unroll
+            for (int w = 0; w < TW; ++w)
+              if (t * 32 + ln < S) rows[(t * 32 + ln) * TW + w] = r[t][w];
+        };
+        if (W == 1) run(std::integral_constant<int, 1>{});
+        else if (W == 2) run(std::integral_constant<int, 2>{});
+        else if (W == 3) run(std::integral_constant<int, 3>{});
+        else run(std::integral_constant<int, 4>{});
+      }
+      sync();
+    }
     uint8_t *brow = smem + L::B + bb * 2 * kTileBytes;
     [[maybe_unused]] float *bias = reinterpret_cast<float *>(smem + L::BIAS) + bb * 1024;
     [[maybe_unused]] const int bstride = kBiasStride * (S > 64 ? 2 : 1);
@@ -1375,7 +1422,7 @@ WsLay ws_layout(const nemb200_dataset *h, int n, bool with_pair) {
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair) { return ws_layout(h, n, with_pair).total; }
 
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                    int impl, cudaStream_t st, int leave_sms_free) {
+                    int impl, cudaStream_t st, int leave_sms_free, int close) {
   NEMB_REQUIRE(h->S >= 8 && h->S <= 128, "tensor-core score needs 8 <= S <= 128 (S=%d)", h->S);
   // AUTO never picks the pair-merged kernel: its score kernel is faster (76 vs 103 us at S=50, E=10k, 1024 graphs)
   // but the per-graph planner costs what it saves (about 20 us per 1024 graphs); callers opt in with TC_PAIR
@@ -1421,6 +1468,8 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   p.kc = (float)(256.0 * kappa2 / 252.0 + h->beta2);
   p.scale = impl == NEMB200_SCORE_TC_EX2_2PASS ? 0.f : (float)h->scale;
   p.plan = nullptr; p.tables = nullptr; p.glist = nullptr; p.n_dev = nullptr;
+  p.close = close ? 1 : 0;
+  NEMB_REQUIRE(!(close && pair), "the pair-merged kernel plans on closed graphs: close them first (nemb200_closure_u32)");
   p.done_counter = nullptr; p.sumN = h->sumN; p.scores = scores;
   // (one CTA finalizing a large batch is slower than the separate, fully parallel kernel; in the two-group MCMC loop
   //  the separate kernel overlaps with the other group's score kernel and the tail of a fused one does not)

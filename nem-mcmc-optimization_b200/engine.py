@@ -223,8 +223,16 @@ class Dataset:
         n_tiles = int(3.0e9 // (self.n_mtiles * 160))  # 160 > the SM count
         return max(per_tile * n_tiles // 1024 * 1024, 1024)
 
-    def score_bits(self, bits: torch.Tensor, impl="auto", out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
-        """Score bit-packed graphs already on the device; returns a float64 CUDA tensor (no sync)."""
+    def _fusable(self, code) -> bool:
+        """closure + score in one launch (nemb200_closure_score_batch): every tensor-core kernel but the pair-merged one."""
+        return self.S >= 8 and code not in (SCORE_IMPLS["witness"], SCORE_IMPLS["pair"])
+
+    def score_bits(self, bits: torch.Tensor, impl="auto", out: torch.Tensor | None = None, stream=None,
+                   close: bool = False) -> torch.Tensor:
+        """Score bit-packed graphs already on the device; returns a float64 CUDA tensor (no sync).
+        close=True: the graphs are not transitively closed yet; the score kernel closes them while it expands its
+        operand (one launch, `bits` is left untouched) - or, for the witness / pair-merged kernels and S < 8, a
+        closed copy is made first."""
         n = int(bits.shape[0])
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=self.device)
@@ -232,11 +240,17 @@ class Dataset:
         code = SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl)
         step = self.max_graphs_per_launch()
         ws, need = self._score_workspace(min(n, step), impl)
+        L = _lib.lib()
+        fused = close and self._fusable(code)
+        if close and not fused and n:
+            closed = torch.empty_like(bits)
+            _lib.check(L.nemb200_closure_u32(_ptr(bits), n, self.S, _ptr(closed), _stream_ptr(st)))
+            bits = closed
+        fn = L.nemb200_closure_score_batch if fused else L.nemb200_score_batch
         for lo in range(0, max(n, 1), step):           # one launch unless the batch exceeds the launch limit
             m = min(step, n - lo)
-            _lib.check(_lib.lib().nemb200_score_batch(self._h, _ptr(bits[lo:lo + m]) if n else _ptr(bits), m,
-                                                      _ptr(out[lo:lo + m]) if n else _ptr(out), _ptr(ws), ws.numel(), code,
-                                                      _stream_ptr(st)))
+            _lib.check(fn(self._h, _ptr(bits[lo:lo + m]) if n else _ptr(bits), m, _ptr(out[lo:lo + m]) if n else _ptr(out),
+                          _ptr(ws), ws.numel(), code, _stream_ptr(st)))
         return out
 
     def score_graphs(self, graphs, impl="auto", close: bool = False) -> np.ndarray:
@@ -245,10 +259,7 @@ class Dataset:
         graphs: (n,S,S) 0/1 adjacency ([a][b]=1 iff a->b) or (n,S,W) uint32 bit rows.
         close=True applies the transitive closure first (create_nem, nem_order_mcmc.py:216-221)."""
         bits = _bits_to_device(graphs, self.S, self.device)
-        if close:
-            st = torch.cuda.current_stream(self.device)
-            _lib.check(_lib.lib().nemb200_closure_u32(_ptr(bits), bits.shape[0], self.S, _ptr(bits), _stream_ptr(st)))
-        return self.score_bits(bits, impl).cpu().numpy()
+        return self.score_bits(bits, impl, close=close).cpu().numpy()
 
     def score_stream(self, host_batches, host_out, close: bool = True, impl="auto"):
         """Score a sequence of equally-sized batches of bit-packed graphs that live in PINNED host memory
@@ -275,13 +286,14 @@ class Dataset:
         P["comp"].wait_stream(cur)
         P["back"].wait_stream(cur)
         code = SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl)
+        fused = close and self._fusable(code)
         for k, hb in enumerate(host_batches):
             b = k & 1
             with torch.cuda.stream(P["copy"]):
                 if k >= 2:
                     P["copy"].wait_event(P["free"][b])      # batch k-2 no longer reads this buffer
                 P["bits"][b].copy_(hb, non_blocking=True)
-                if close:  # the closure of batch k+1 also runs beside the score kernel of batch k
+                if close and not fused:  # (witness / pair-merged kernels: a separate closure, beside the score kernel of batch k)
                     _lib.check(L.nemb200_closure_u32(_ptr(P["bits"][b]), n, self.S, _ptr(P["bits"][b]), _stream_ptr(P["copy"])))
                 P["ready"][b].record(P["copy"])
             with torch.cuda.stream(P["comp"]):
@@ -289,8 +301,9 @@ class Dataset:
                 if k >= 2:
                     P["comp"].wait_event(P["drained"][b])   # the scores of batch k-2 have left this buffer
                 bits = P["bits"][b]
-                _lib.check(L.nemb200_score_batch(self._h, _ptr(bits), n, _ptr(P["scores"][b]), _ptr(P["ws"]), P["ws"].numel(),
-                                                 code, _stream_ptr(P["comp"])))
+                fn = L.nemb200_closure_score_batch if fused else L.nemb200_score_batch   # fused: closure inside the score kernel
+                _lib.check(fn(self._h, _ptr(bits), n, _ptr(P["scores"][b]), _ptr(P["ws"]), P["ws"].numel(), code,
+                              _stream_ptr(P["comp"])))
                 P["free"][b].record(P["comp"])
             with torch.cuda.stream(P["back"]):               # scores go back on their own stream, off the kernels' path
                 P["back"].wait_event(P["free"][b])

@@ -348,6 +348,30 @@ def test_order_to_graph_vs_oracle(nb, S):
             assert np.array_equal(got[c], orc.order_to_graph(orders[c], rule, cand, use_nem)), (rule, use_nem, c)
 
 
+@pytest.mark.parametrize("S,E,n,impl", [(10, 100, 37, "auto"), (20, 300, 64, "auto"), (50, 1000, 130, "lut"), (50, 1000, 9, "ex2_2pass"),
+                                        (33, 257, 21, "auto"), (64, 300, 17, "auto"), (100, 700, 23, "lutm"), (128, 200, 9, "auto")])
+def test_closure_fused_into_score_kernel(nb, S, E, n, impl):
+    """nemb200_closure_score_batch (closure inside the score kernel's operand expansion, one launch) == closure kernel +
+    score kernel == the oracle's closure + score, on unclosed DAGs and on digraphs with cycles; the input is not modified."""
+    _, _, D = orc.synth_dataset(S, E, seed=S)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rng = np.random.default_rng(S + n)
+    raw = np.stack([orc.order_to_graph(rng.permutation(S), 1, rng.random((S, S)) < 0.15, False) for _ in range(n)]).astype(np.uint8)
+    raw[-1] = (rng.random((S, S)) < 0.03).astype(np.uint8)          # an arbitrary digraph (cycles)
+    ds = nb.Dataset(D, A, B)
+    bits = torch.from_numpy(nb.pack_adj(raw).view(np.int32)).cuda()
+    keep = bits.clone()
+    fused = ds.score_bits(bits, impl=impl, close=True).cpu().numpy()
+    assert torch.equal(bits, keep)
+    two = ds.score_bits(nb.closure(bits, S=S, return_bits=True), impl=impl).cpu().numpy()
+    assert np.array_equal(fused, two)                                # same kernel, same operand: bit-identical
+    ref = c_oracle.score_batch(np.stack([c_oracle.closure(g) for g in raw]), D, A, B)
+    assert np.allclose(fused, ref, rtol=1e-6)
+    assert np.allclose(ds.score_graphs(raw, close=True, impl=impl), ref, rtol=1e-6)
+    # the implementations that cannot fuse fall back to closure + score
+    assert np.allclose(ds.score_graphs(raw, close=True, impl="witness"), ref, rtol=1e-11)
+
+
 # --------------------------------------------------------------------------------------------- MCMC
 def _compare_chain(res, c, ref, S, tol=1e-6):
     assert res.accept_counts[c] == ref["n_accept"]

@@ -139,6 +139,11 @@ bits = torch.arange(lo, hi, dtype=torch.int32)[:, None, None].repeat(1, S, W)
 score, chain, order, b = parallel.global_best(best, orders, bits, lo)
 assert score == -1.0 and chain == 5 and int(order[0]) == 5 and int(b[0, 0]) == 5
 assert parallel.allreduce_sum_scalar(float(rank + 1), "cpu") == 3.0
+# SURVEY 8e: the data matrix travels once, rank 0 -> all (bit-packed)
+rng = np.random.default_rng(5)
+D0 = (rng.random((7, 45)) < 0.4).astype(np.uint8)
+d, A, B = parallel.broadcast_dataset(D0 if rank == 0 else None, -2.89 if rank == 0 else None, -2.25 if rank == 0 else None, src=0, device="cpu")
+assert d.shape == (7, 45) and np.array_equal(d, D0) and (A, B) == (-2.89, -2.25)
 dist.destroy_process_group()
 print("ok", rank)
 """
