@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) k_mcmc_fused(const FusedParams p) {
     if (kThreads <= 320 || tid == 0) {
       double v = 0.0;
       for (int w8 = 2; w8 < kThreads / 32; ++w8) v += sRed[w8];
-      const double ll = sumN + NEMB200_LN2 * v;
+      const double ll = __fma_rn(NEMB200_LN2, v, sumN);  // (explicit, like the score kernel's finalize: identical roundings on both MCMC paths)
       bool acc_ok, better;
       if (init) {
         acc_ok = true; better = true;

@@ -251,6 +251,7 @@ __device__ __forceinline__ void wg_bar_sync(int wg) {
 // CTA, so every CTA gets the same number of tiles (+-1) whatever the batch size.  A CTA's range is a
 // sequence of "items" (runs of E tiles inside one N tile: one B-operand expansion each); an N tile cut by CTA
 // boundaries gives one partial sum per piece ("slot" = CTA index - first CTA of that N tile).
+constexpr int kShortFirstItem = 16;  // tiles: below this the CTA's second operand is expanded in the prologue as well
 constexpr int kMinTilesPerCta = 20;  // a CTA gets at least ceil(n_mtiles / 20) tiles: at most 22 slots per N tile
 constexpr int kMaxSlots = 24;
 __host__ __device__ inline int effective_ctas(unsigned T, int n_mtiles, int max_ctas) {
@@ -299,6 +300,19 @@ __device__ __forceinline__ int item_slot(int ntile, int n_ntiles, int n_mtiles, 
 #define DBG(flag) (p.debug & (flag))
 #else
 #define DBG(flag) false
+#endif
+// development: -DNEMB200_PHASES + NEMB200_DEBUG=32 -> %globaltimer stamps of CTA 0's phases at trace[8000 + k]
+#ifdef NEMB200_PHASES
+#define PHASE(k)                                                                                          \
+  do {                                                                                                    \
+    if (p.trace != nullptr && blockIdx.x == 0) {                                                          \
+      unsigned long long t_;                                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                              \
+      p.trace[8000 + (k)] = (long long)t_;                                                                \
+    }                                                                                                     \
+  } while (0)
+#else
+#define PHASE(k)
 #endif
 #ifndef NEMB200_TRACE
 #define TRACE(role, tile, ev)
@@ -739,6 +753,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
   extern __shared__ __align__(1024) uint8_t smem[];
   if (p.n_dev != nullptr && *p.n_dev == 0) return;  // list mode with an empty list: nothing to do (uniform exit)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) PHASE(0);
   const uint32_t sbase = smem_u32(smem);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::BAR);
   // barrier map: a_full[4] a_empty[4] t_full[2] t_empty[2] b_full[2] e_done[2]
@@ -777,6 +792,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) PHASE(1);
   const uint32_t tmem_base = *s_tmem;
   const int S = p.S, W = p.W, G = p.G;
   // list mode: the graph count (and with it the item count) is only known on the device
@@ -829,44 +845,90 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     [[maybe_unused]] float *bias = reinterpret_cast<float *>(smem + L::BIAS) + bb * 1024;
     [[maybe_unused]] const int bstride = kBiasStride * (S > 64 ? 2 : 1);
     const int CS = p.CS;
-    // padding sites (S <= j < CS) of the specialised kernels look up a table entry that is zero:
-    // offset 128*m with m odd is entry [q=(m-1)/2][p=32], zero as soon as 32 + (m-1)/2 > S
+    // ---- phase 1: rows -> columns.  A warp holds a staged graph one row (or W rows) per lane and transposes it as
+    // 32 x 32 bit blocks (five shuffle-xor butterfly steps per block): afterwards lane j holds, for column j, j+32, ..,
+    // the mask of the rows that have an edge into it - the ancestor mask of site j.  The masks go back in place
+    // (sRows[gi][j][w]; the rows are not needed any more).  ~40 instructions per block instead of a 50-iteration
+    // bit-gather loop per column.
+    {
+      const int wi = te >> 5, nw = nthr >> 5, ln = te & 31;
+      for (int gi = wi; gi < ng; gi += nw) {
+        uint32_t *rows = sRows + gi * gw;
+        auto run = [&](auto tw_c) {
+          constexpr int TW = decltype(tw_c)::value;
+          uint32_t x[TW][TW];  // x[t][w]: word w of row t*32 + lane
+#pragma unroll
+          for (int t = 0; t < TW; ++t)
+#pragma unroll
+            for (int w = 0; w < TW; ++w) x[t][w] = (t * 32 + ln < S) ? rows[(t * 32 + ln) * TW + w] : 0u;
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < TW; ++t)
+#pragma unroll
+            for (int w = 0; w < TW; ++w) {
+              uint32_t v = x[t][w];
+#pragma unroll
+              for (int sft = 16; sft > 0; sft >>= 1) {
+                const uint32_t m = sft == 16 ? 0x0000FFFFu : (sft == 8 ? 0x00FF00FFu : (sft == 4 ? 0x0F0F0F0Fu : (sft == 2 ? 0x33333333u : 0x55555555u)));
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, v, sft);
+                v = (ln & sft) ? ((v & ~m) | ((y >> sft) & m)) : ((v & m) | ((y << sft) & ~m));
+              }
+              x[t][w] = v;  // now: rows t*32.. of column w*32 + lane
+            }
+          // column j = w*32 + lane: word t of its mask = x[t][w]; the site itself belongs to its ancestor-or-self set
+#pragma unroll
+          for (int w = 0; w < TW; ++w) {
+            const int j = w * 32 + ln;
+            if (j < S) {
+#pragma unroll
+              for (int t = 0; t < TW; ++t) rows[j * TW + t] = x[t][w] | ((t == w) ? (1u << ln) : 0u);
+            }
+          }
+        };
+        if (W == 1) run(std::integral_constant<int, 1>{});
+        else if (W == 2) run(std::integral_constant<int, 2>{});
+        else if (W == 3) run(std::integral_constant<int, 3>{});
+        else run(std::integral_constant<int, 4>{});
+      }
+    }
+    sync();
+    // ---- phase 2: masks -> operand bytes, one (column, 16-byte chunk of K) per step.  Only the K bytes the MMA reads
+    // are written (ksteps x 32 per row).  Padding sites (S <= j < CS) of the specialised kernels look up a table entry
+    // that is zero: offset 128*m with m odd is entry [q=(m-1)/2][p=32], zero as soon as 32 + (m-1)/2 > S.
     const uint32_t zero_m = S < 32 ? 1u : (uint32_t)(2 * (S - 32) + 3);
-    for (int col = te; col < (DBG(8) ? 0 : 256); col += nthr) {
+    const int nch = 2 * p.ksteps;
+    for (int idx = te; idx < (DBG(8) ? 0 : 256 * nch); idx += nthr) {
+      const int col = idx / nch, c = idx - col * nch;
       const int gi = col / CS, j = col - gi * CS;
-      uint32_t anc[4] = {0u, 0u, 0u, 0u};
-      int cnt = 0;
       const bool used = gi < ng && j < S;
+      int cnt = 0;
+      uint32_t half = 0;
       if (used) {
-        const uint32_t *rows = sRows + gi * S * W;
-        const int jw = j >> 5, jb = j & 31;
-        for (int a = 0; a < S; ++a) {
-          uint32_t bit = ((rows[a * W + jw] >> jb) & 1u) | (a == j ? 1u : 0u);
-          anc[a >> 5] |= bit << (a & 31);
-          cnt += (int)bit;
-        }
+        const uint32_t *mk = sRows + gi * gw + j * W;
+        for (int w = 0; w < W; ++w) cnt += __popc(mk[w]);
+        half = (c >> 1) < W ? ((mk[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) : 0u;
       }
       // table look-up sites get the extra K row S: B = lut_base/128 (A holds 128 there), so that the
       // accumulator is the shared-memory address of lut[q][p]; unused columns point at lut[0][0]
       bool lut_site = EPI == EPI_LUT && gi < G;
       if constexpr (S_T > 0) lut_site = lut_site && is_lut_site<S_T, NLUT>(j);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t half = (anc[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-        uint4 v;
-        constexpr int sh = EPI == EPI_LUTM ? 0 : 1;  // operand value 2 (the A operand tells D=1 from D=0); LUTM: 1 (A = 4*D)
-        v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
-        v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
-        v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
-        v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
-        if (lut_site && c == (S >> 4)) {
-          uint32_t extv = ((sbase + L::LUT) >> 7) + (j >= S ? zero_m : 0u);
-          if (extv > 255u) asm volatile("trap;");  // the table must sit in the first 32 KB of shared memory
-          uint32_t ext = extv << ((S & 3) * 8);
-          int wsel = (S >> 2) & 3;
-          if (wsel == 0) v.x |= ext; else if (wsel == 1) v.y |= ext; else if (wsel == 2) v.z |= ext; else v.w |= ext;
+      uint4 v;
+      constexpr int sh = EPI == EPI_LUTM ? 0 : 1;  // operand value 2 (the A operand tells D=1 from D=0); LUTM: 1 (A = 4*D)
+      v.x = (((half & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
+      v.y = ((((half >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
+      v.z = ((((half >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
+      v.w = ((((half >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) << sh;
+      auto put_byte = [&](int k, uint32_t val) {  // byte k of the row, if it lies in this chunk
+        if ((k >> 4) == c) {
+          const uint32_t e = val << ((k & 3) * 8);
+          const int wsel = (k >> 2) & 3;
+          if (wsel == 0) v.x |= e; else if (wsel == 1) v.y |= e; else if (wsel == 2) v.z |= e; else v.w |= e;
         }
-        *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
+      };
+      if (lut_site) {
+        const uint32_t extv = ((sbase + L::LUT) >> 7) + (j >= S ? zero_m : 0u);
+        if (extv > 255u) asm volatile("trap;");  // the table must sit in the first 32 KB of shared memory
+        put_byte(S, extv);
       }
       if constexpr (EPI == EPI_LUTM) {
         // constant K rows (A operand: 128 in rows S and S+1, 4 in row S+2): the byte address of the column's first
@@ -874,14 +936,15 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
         const uint32_t addr = sbase + L::LUT + 4u * (uint32_t)(used ? cnt * (cnt + 1) / 2 : NEMB200_LUTM_ZERO);
         const uint32_t q = addr >> 7, b0 = q < 255u ? q : 255u;
         if (q - b0 > 255u) asm volatile("trap;");  // level 0 must sit in the first 64 KB of shared memory
-        brow[sw128((uint32_t)col, (uint32_t)S)] = (uint8_t)b0;
-        brow[sw128((uint32_t)col, (uint32_t)(S + 1))] = (uint8_t)(q - b0);
-        brow[sw128((uint32_t)col, (uint32_t)(S + 2))] = (uint8_t)((addr & 127u) >> 2);
+        put_byte(S, b0);
+        put_byte(S + 1, q - b0);
+        put_byte(S + 2, (addr & 127u) >> 2);
       } else {
         // (specialised mixed kernels convert the accumulator with the 2^14 magic number, see kMagic14)
-        if (gi < G && j < kBiasStride * 2)
+        if (c == 0 && gi < G && j < kBiasStride * 2)
           bias[gi * bstride + j] = p.kc * (float)cnt - p.scale - ((S_T > 0 && NLUT < S_T) ? p.k1 * 16384.f : 0.f);
       }
+      *reinterpret_cast<uint4 *>(brow + sw128((uint32_t)col, (uint32_t)c * 16u)) = v;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   };
@@ -896,6 +959,18 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
                    [] { asm volatile("bar.sync 7, %0;" ::"n"(kWideThreads) : "memory"); });
         asm volatile("bar.sync 7, %0;" ::"n"(kWideThreads) : "memory");  // every column is written and fenced
         if (warp < 4 && lane == 0) mbar_arrive(bar_bfull);               // the two arrivals the barrier expects
+        if (threadIdx.x == 64) PHASE(2);
+        // A CTA whose range starts just before an N-tile boundary has a first item of a few tiles only: the two
+        // expander warps (lowest scheduling priority of the CTA) cannot finish the second operand behind it and the
+        // whole CTA would wait for them (measured: such CTAs finished 6-9 us late).  Expand that one here too.
+        Item i1;
+        if (i0.nt < kShortFirstItem && wk0.next(i1, p.n_mtiles)) {
+          const int g1 = i1.ntile * G;
+          expand_std(g1, min(G, n_graphs - g1), 1u, (int)threadIdx.x - 64, kWideThreads,
+                     [] { asm volatile("bar.sync 7, %0;" ::"n"(kWideThreads) : "memory"); });
+          asm volatile("bar.sync 7, %0;" ::"n"(kWideThreads) : "memory");
+          if (warp < 4 && lane == 0) mbar_arrive(bar_bfull + 8);
+        }
       }
     }
   }
@@ -960,12 +1035,14 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     const int te = threadIdx.x - 64;
     Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
     Item im;
+    [[maybe_unused]] int first_nt = 0;
     for (int k = 0; wk.next(im, p.n_mtiles); ++k) {
       const int ntile = im.ntile;
       const int g0 = ntile * G, ng = min(G, n_graphs - g0);
       const uint32_t bb = k & 1u;
       if (k >= 2) mbar_wait(bar_edone + 8 * bb, ((k - 2) >> 1) & 1u);  // epilogue finished the item that used this buffer
-      if (!PAIR && k == 0) continue;  // expanded by all warps above
+      if (!PAIR && k == 0) { first_nt = im.nt; continue; }        // expanded by all warps above
+      if (!PAIR && k == 1 && first_nt < kShortFirstItem) continue;  // ... and so was this one (short first item)
       if constexpr (!PAIR) expand_std(g0, ng, bb, te, 64, [] { asm volatile("bar.sync 6, 64;" ::: "memory"); });
       else asm volatile("bar.sync 6, 64;" ::: "memory");
       uint8_t *brow = smem + L::B + bb * 2 * kTileBytes;
@@ -1045,7 +1122,12 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       const int ng_mine = gl < G ? max(0, min(gq, n_graphs - g0)) : 0;
       const uint32_t bb = k & 1u, bbph = (k >> 1) & 1u;
       const float *bias = reinterpret_cast<const float *>(smem + L::BIAS) + bb * 1024 + gl * bstride;
+      // partial-sum slot of this CTA inside the item's N tile (two emulated divisions: computed up front by the few
+      // threads that store partial sums, not between the item's last tile and its hand-over)
+      int slot = 0;
+      if (tw < kMaxG / 4) slot = item_slot(ntile, n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
       mbar_wait(bar_bfull + 8 * bb, bbph);  // bias values (pair kernel: tables) of this item are written
+      if (threadIdx.x == 128 && k == 0) PHASE(3);
       double part[kMaxG / 4];
 #pragma unroll
       for (int g = 0; g < kMaxG / 4; ++g) part[g] = 0.0;
@@ -1098,14 +1180,29 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       if (tw < ng_out) {
         double v = 0.0;
         for (int w4 = 0; w4 < 4; ++w4) v += sRed[(wg * 4 + w4) * 8 + tw];
-        p.partials[(size_t)(g0 + tw) * p.n_slots + item_slot(ntile, n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x)] = v;  // list mode: indexed by list position
-        if (p.done_counter != nullptr) __threadfence();  // visible to the CTA that finalizes (below)
+        p.partials[(size_t)(g0 + tw) * p.n_slots + slot] = v;  // list mode: indexed by list position
+        // (no gpu-scope fence per item - it would stall the warpgroup; every thread fences ONCE, before the barrier at
+        //  the end of the kernel, see below)
       }
       wg_bar_sync(wg);
     }
   }
+  if (threadIdx.x == 128) PHASE(4);
+  // fused finalize: the partial sums this CTA stored must be visible gpu-wide before thread 0 reports in (a fence by
+  // thread 0 alone does not cover the other threads' stores: each storing thread fences, then the CTA barrier)
+  if (p.done_counter != nullptr) __threadfence();
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) PHASE(5);
+#ifdef NEMB200_PHASES
+  if (threadIdx.x == 0 && p.trace != nullptr) {  // every CTA: when it finished, when it started, on which SM
+    unsigned long long t_; unsigned sm_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+    p.trace[7600 + blockIdx.x] = (long long)t_;
+    p.trace[7800 + blockIdx.x] = (long long)sm_;
+  }
+#endif
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   if (p.done_counter != nullptr) {
     // ---- fused finalize ("last block" pattern): score = sum_e N[e] + ln2 * sum of the graph's partial sums
@@ -1122,13 +1219,23 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       for (int g = threadIdx.x; g < n_graphs; g += cta_threads(S_T)) {
         const int cnt = slots_of_ntile(g / G, p.n_mtiles, T, (int)gridDim.x);
         const double *src = p.partials + (size_t)g * p.n_slots;
-        double v = 0.0;
-        for (int c = 0; c < cnt && c < p.n_slots; ++c) v += __ldcg(src + c);
-        p.scores[g] = sumN + NEMB200_LN2 * v;
+        // (the first four slots - all there are unless E is huge - are fetched together: one L2 round trip, same order of additions)
+        const double s0 = __ldcg(src), s1 = cnt > 1 ? __ldcg(src + 1) : 0.0, s2 = cnt > 2 ? __ldcg(src + 2) : 0.0,
+                     s3 = cnt > 3 ? __ldcg(src + 3) : 0.0;
+        double v = s0;
+        if (cnt > 1) v += s1;
+        if (cnt > 2) v += s2;
+        if (cnt > 3) v += s3;
+        for (int c = 4; c < cnt && c < p.n_slots; ++c) v += __ldcg(src + c);
+        p.scores[g] = __fma_rn(NEMB200_LN2, v, sumN);  // (explicit: both finalize paths must round alike)
       }
       if (threadIdx.x == 0) *p.done_counter = 0;  // ready for the next launch on this workspace
+#ifdef NEMB200_PHASES
+      if (threadIdx.x == 0 && p.trace != nullptr) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[8007] = (long long)t_; p.trace[8008] = blockIdx.x; }
+#endif
     }
   }
+  if (threadIdx.x == 0) PHASE(6);
 }
 
 // ---- pair planner --------------------------------------------------------------------------------------
@@ -1346,7 +1453,7 @@ __global__ void k_finalize(const double *partials, int n_slots, int G, int n_mti
   const int cnt = slots_of_ntile(idx / tiles_g, n_mtiles, T, effective_ctas(T, n_mtiles, max_ctas));
   double v = 0.0;
   for (int c = 0; c < cnt && c < n_slots; ++c) v += src[c];
-  scores[g] = *sumN + NEMB200_LN2 * v;
+  scores[g] = __fma_rn(NEMB200_LN2, v, *sumN);  // (explicit: both finalize paths must round alike)
 }
 
 int num_sms() {
