@@ -129,6 +129,13 @@ int nemb200_cell_ll(const double *d_cell, int rows, int E, double *d_order_weigh
  *      touching the swapped nodes as in :190-194), 0 = copy the weight through.  d_out_weights[i][k] = the
  *      minimiser of the objective in s = expit(x) over [0,1] (what the reference thresholds at 0.5, :212).  The
  *      reference stops L-BFGS-B at tol=0.01; this returns the exact global minimiser. */
+/* ---- ancestor_x of get_optimal_weights (nem_order_mcmc.py:185): clip((I - expit_parent_weights(W))^-1 - I, 0, 1), the
+ *      reference's scipy.linalg.inv call, on the device (one CTA: in-place Gauss-Jordan with partial pivoting in shared
+ *      memory, S <= 128).  d_weights: S x S float64 raw weights; d_permissible: uint8 S x S, 1 where k is a permissible
+ *      parent of i (expit is applied to those entries only, :152-157); d_out: S x S float64; *d_singular (int, device) is set to 1 if a pivot vanishes (never for weights that respect an order). */
+int nemb200_ancestor_x(const double *d_weights, const uint8_t *d_permissible, int S, double *d_out,
+                       int *d_singular, void *stream);
+
 int nemb200_fit_edges(const nemb200_dataset *h, const double *d_weights, const double *d_order_weights,
                       const double *d_ancestor_x, const uint8_t *d_mask, double *d_out_weights,
                       void *stream);

@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
     L.nemb200_cell_ll_workspace_bytes.argtypes = [i32]
     L.nemb200_cell_ll.argtypes = [vp, i32, i32, vp, vp, vp, sz, vp]
     L.nemb200_synth_knockdown.argtypes = [vp, vp, i32, i32, dbl, dbl, u64, vp, vp, vp]
+    L.nemb200_ancestor_x.argtypes = [vp, vp, i32, vp, vp, vp]
     L.nemb200_fit_edges.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.nemb200_selftest_partition.argtypes = [i32, i32, i32]
     _lib = L
@@ -86,7 +87,7 @@ EXPORTS = ["nemb200_version", "nemb200_last_error", "nemb200_dataset_bytes", "ne
            "nemb200_score_workspace_bytes", "nemb200_score_workspace_bytes_impl", "nemb200_score_batch", "nemb200_closure_score_batch", "nemb200_order_to_graph",
            "nemb200_mcmc_workspace_bytes", "nemb200_mcmc_run", "nemb200_replica_exchange", "nemb200_replica_exchange_best",
            "nemb200_edge_counts_reduce", "nemb200_cell_ratios", "nemb200_cell_ll_workspace_bytes",
-           "nemb200_cell_ll", "nemb200_synth_knockdown", "nemb200_fit_edges", "nemb200_selftest_partition"]
+           "nemb200_cell_ll", "nemb200_synth_knockdown", "nemb200_ancestor_x", "nemb200_fit_edges", "nemb200_selftest_partition"]
 
 
 def check(rc: int) -> None:

@@ -232,6 +232,78 @@ __global__ void __launch_bounds__(kFitThreads) k_fit_edges(const uint32_t *__res
 }
 }  // namespace
 
+// ---- ancestor_x of get_optimal_weights (nem_order_mcmc.py:185): clip((I - expit_parent_weights(W))^-1 - I, 0, 1).
+// One CTA inverts the S x S matrix in shared memory: in-place Gauss-Jordan with partial (row) pivoting, the column
+// permutation undone at the end - what scipy.linalg.inv's LU does for the reference, without leaving the device.
+// (For weights that respect an order I - expit(W) is a permuted unit-triangular matrix: every pivot is exactly 1.)
+namespace {
+constexpr int kInvThreads = 256;
+__global__ void __launch_bounds__(kInvThreads) k_ancestor_x(const double *__restrict__ weights, const uint8_t *__restrict__ perm,
+                                                            int S, double *__restrict__ out, int *__restrict__ singular) {
+  extern __shared__ double a[];  // S x S
+  __shared__ int piv[NEMB200_MAX_S];
+  __shared__ double red_v[kInvThreads];
+  __shared__ int red_i[kInvThreads];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < S * S; i += kInvThreads) {
+    const double w = weights[i];
+    const double e = perm[i] ? 1.0 / (1.0 + exp(-w)) : w;  // expit on the permissible parents only (:152-157)
+    a[i] = ((i / S) == (i % S) ? 1.0 : 0.0) - e;
+  }
+  __syncthreads();
+  for (int c = 0; c < S; ++c) {
+    // pivot: the row r >= c with the largest |a[r][c]|
+    double bv = -1.0; int bi = c;
+    for (int r = c + tid; r < S; r += kInvThreads) { const double v = fabs(a[r * S + c]); if (v > bv) { bv = v; bi = r; } }
+    red_v[tid] = bv; red_i[tid] = bi;
+    __syncthreads();
+    for (int o = kInvThreads / 2; o > 0; o >>= 1) {
+      if (tid < o && (red_v[tid + o] > red_v[tid] || (red_v[tid + o] == red_v[tid] && red_i[tid + o] < red_i[tid]))) {
+        red_v[tid] = red_v[tid + o]; red_i[tid] = red_i[tid + o];
+      }
+      __syncthreads();
+    }
+    const int r = red_i[0];
+    if (tid == 0) { piv[c] = r; if (!(red_v[0] > 0.0)) *singular = 1; }
+    if (r != c) for (int j = tid; j < S; j += kInvThreads) { const double t = a[c * S + j]; a[c * S + j] = a[r * S + j]; a[r * S + j] = t; }
+    __syncthreads();
+    const double p = a[c * S + c];
+    __syncthreads();
+    for (int j = tid; j < S; j += kInvThreads) a[c * S + j] = (j == c ? 1.0 : a[c * S + j]) / p;
+    __syncthreads();
+    // eliminate column c from every other row (the column itself becomes -f / p, the in-place inverse update)
+    for (int idx = tid; idx < S * S; idx += kInvThreads) {
+      const int i = idx / S, j = idx - i * S;
+      if (i == c) continue;
+      const double f = a[i * S + c];
+      if (j != c) a[idx] -= f * a[c * S + j];
+    }
+    __syncthreads();
+    for (int i = tid; i < S; i += kInvThreads) if (i != c) a[i * S + c] = -a[i * S + c] * a[c * S + c];
+    __syncthreads();
+  }
+  for (int c = S - 1; c >= 0; --c) {  // undo the row exchanges as column exchanges
+    const int r = piv[c];
+    if (r != c) for (int i = tid; i < S; i += kInvThreads) { const double t = a[i * S + c]; a[i * S + c] = a[i * S + r]; a[i * S + r] = t; }
+    __syncthreads();
+  }
+  for (int i = tid; i < S * S; i += kInvThreads) {
+    const double v = a[i] - ((i / S) == (i % S) ? 1.0 : 0.0);
+    out[i] = fmin(fmax(v, 0.0), 1.0);
+  }
+}
+}  // namespace
+
+extern "C" int nemb200_ancestor_x(const double *d_weights, const uint8_t *d_permissible, int S, double *d_out,
+                                  int *d_singular, void *stream) {
+  NEMB_REQUIRE(d_weights && d_permissible && d_out && S >= 1 && S <= NEMB200_MAX_S, "bad arguments");
+  const size_t smem = sizeof(double) * (size_t)S * S;
+  NEMB_CHECK_CUDA(cudaFuncSetAttribute(k_ancestor_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_ancestor_x<<<1, kInvThreads, smem, (cudaStream_t)stream>>>(d_weights, d_permissible, S, d_out, d_singular);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int nemb200_fit_edges(const nemb200_dataset *h, const double *d_weights, const double *d_order_weights,
                                  const double *d_ancestor_x, const uint8_t *d_mask, double *d_out_weights, void *stream) {
   NEMB_REQUIRE(h && d_weights && d_order_weights && d_ancestor_x && d_mask && d_out_weights, "null argument");

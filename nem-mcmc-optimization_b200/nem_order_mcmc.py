@@ -135,18 +135,30 @@ class NEMOrderMCMC:
         ow = torch.empty_like(cell)
         _lib.check(L.nemb200_cell_ll(engine._ptr(cell), S + 1, E, engine._ptr(ow), engine._ptr(ll), engine._ptr(ws),
                                      ws.numel(), engine._stream_ptr(st)))
-        # ancestor_x (:185): clip((I - expit(W))^-1 - I, 0, 1), an S x S inverse on the device
-        wexp = torch.from_numpy(self.expit_parent_weights(W)).to(dev)
-        eye = torch.eye(S, dtype=torch.float64, device=dev)
-        anc = torch.clamp(torch.linalg.inv(eye - wexp) - eye, 0.0, 1.0).contiguous()
+        # ancestor_x (:185): clip((I - expit(W))^-1 - I, 0, 1): in-kernel Gauss-Jordan (nemb200_ancestor_x), no library call
         wraw = torch.from_numpy(np.ascontiguousarray(W)).to(dev)
+        pm = torch.from_numpy(np.ascontiguousarray(perm)).to(dev)
+        anc = torch.empty((S, S), dtype=torch.float64, device=dev)
+        sing = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(L.nemb200_ancestor_x(engine._ptr(wraw), engine._ptr(pm), S, engine._ptr(anc), engine._ptr(sing),
+                                        engine._stream_ptr(st)))
         mk = torch.from_numpy(np.ascontiguousarray(mask)).to(dev)
         out = torch.empty((S, S), dtype=torch.float64, device=dev)
         _lib.check(L.nemb200_fit_edges(self.nem.dataset._h, engine._ptr(wraw), engine._ptr(ow), engine._ptr(anc),
                                        engine._ptr(mk), engine._ptr(out), engine._stream_ptr(st)))
-        self.ancestor_x = anc.cpu().numpy()
+        # the whole pass (cell ratios -> posterior -> inverse -> fits) is queued on one stream; ONE host read at the end
+        res = torch.cat([out.reshape(-1), ll, sing.to(torch.float64)]).cpu().numpy()
+        if res[-1] != 0.0:
+            raise _lib.NemB200Error("ancestor_x: I - expit(W) is singular")
+        self._ancestor_x_dev = anc
         self.order_weights = ow  # device tensor (S+1, E)
-        return out.cpu().numpy(), float(ll.item())
+        return res[:S * S].reshape(S, S), float(res[S * S])
+
+    @property
+    def ancestor_x(self):
+        """clip((I - expit(W))^-1 - I, 0, 1) of the last fit pass (:185), fetched from the device on demand."""
+        a = getattr(self, "_ancestor_x_dev", None)
+        return None if a is None else a.cpu().numpy()
 
     def calculate_local_optimum(self, i, k):
         """nem_order_mcmc.py:160-170 for one pair (the batched form is fit_weights)."""

@@ -670,6 +670,40 @@ def test_network_csv_round_trip(nb, tmp_path):
     assert f.read_bytes().count(b"\r\n") == closed.sum() + 3
 
 
+@pytest.mark.parametrize("S", [5, 20, 64, 128])
+def test_ancestor_x_inverse_vs_numpy(nb, S):
+    """nemb200_ancestor_x = clip(inv(I - expit_parent_weights(W)) - I, 0, 1) (nem_order_mcmc.py:185, :152-157): the
+    in-kernel Gauss-Jordan against numpy's LU inverse, for weights that respect an order (every pivot 1) and for a
+    general matrix whose inversion needs row exchanges."""
+    import ctypes as C
+    from scipy.special import expit
+    L = nb._lib.lib()
+    rng = np.random.default_rng(S)
+    order = rng.permutation(S)
+    pos = np.argsort(order)
+    perm = (pos[None, :] < pos[:, None]).astype(np.uint8)        # k permissible parent of i iff k comes earlier
+    for case in ("order", "general"):
+        W = rng.normal(size=(S, S))
+        if case == "order":
+            W = W * perm
+            pm = perm
+        else:
+            pm = (rng.random((S, S)) < 0.5).astype(np.uint8)
+            W[np.arange(S), np.arange(S)] = 1.0 + rng.random(S)  # I - W: small / negative diagonal -> pivoting
+            W *= 0.9
+        M = np.where(pm != 0, expit(W), W)
+        ref = np.clip(np.linalg.inv(np.eye(S) - M) - np.eye(S), 0.0, 1.0)
+        wt = torch.from_numpy(W).cuda()
+        pt = torch.from_numpy(pm).cuda()
+        out = torch.empty((S, S), dtype=torch.float64, device="cuda")
+        sing = torch.zeros(1, dtype=torch.int32, device="cuda")
+        nb._lib.check(L.nemb200_ancestor_x(C.c_void_p(wt.data_ptr()), C.c_void_p(pt.data_ptr()), S, C.c_void_p(out.data_ptr()),
+                                           C.c_void_p(sing.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        assert int(sing.item()) == 0
+        cond = np.linalg.cond(np.eye(S) - M)
+        assert np.allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-12 * max(1.0, cond)), (case, cond)
+
+
 def test_device_synthesis_vs_oracle(nb):
     """nemb200_synth_knockdown is bit-exact against the oracle restatement of utils.py:15-35 driven
     by the same Philox stream, and has the flip rates alpha / beta at a large shape."""
