@@ -223,6 +223,19 @@ def edge_fit_leg(nb, synth, with_cpu):
     torch.cuda.synchronize()
     row = {"config": "S=20 E=1000, one pass = 190 edge fits", "gpu_ms_per_pass": (time.perf_counter() - t0) / reps * 1e3,
            "semantics": "exact minimiser of nem_order_mcmc.py:18-23 per edge (reference: scipy L-BFGS-B stopped at tol=0.01)"}
+    # the same step inside the device-resident loop (NEMB200_RULE_FIT): 64 chains of BASELINE config 2's shape, every
+    # iteration = propose + reset + 190 fits + threshold + soft score + accept per chain, no host synchronisation
+    n_ch, it_fit = 64, 32
+    st = nb.ChainState(nm.dataset, synth.random_orders(n_ch, s, 1), 2.0 * s / e, edge_counts=True, seed=1234, rule=nb.RULE_FIT, use_nem=False)
+    st.run(16)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(); st.run(it_fit); ev1.record(); torch.cuda.synchronize()
+    ms_fit = ev0.elapsed_time(ev1)
+    row["device_loop"] = {"chains": n_ch, "iters": it_fit, "ms_per_iteration": ms_fit / it_fit,
+                          "chain_iterations_per_s": n_ch * it_fit / (ms_fit * 1e-3),
+                          "accept_rate": float(st.accept.sum().item()) / (n_ch * st.iters_done),
+                          "note": "rule FIT in nemb200_mcmc_run: the reference's order->DAG step for all chains at once, zero host syncs in the loop"}
     if with_cpu:
         from oracle import nem_oracle as orc
         t0 = time.perf_counter()

@@ -34,7 +34,13 @@ extern "C" {
 #define NEMB200_VERSION 1
 #define NEMB200_MAX_S 128
 
-enum { NEMB200_RULE_FULL = 0, NEMB200_RULE_MASKED = 1 };
+enum {
+  NEMB200_RULE_FULL = 0,   /* W = permissibility mask of the order */
+  NEMB200_RULE_MASKED = 1, /* W = permissibility & candidate-edge mask */
+  NEMB200_RULE_FIT = 2     /* nemb200_mcmc_run only: the reference's own order -> DAG step - per-order edge-weight fit
+                              (get_optimal_weights, nem_order_mcmc.py:172-208) + threshold, scored with the driver's
+                              expit-on-weights cell ratios (:207), all chains at once on the device */
+};
 /* score implementations (nemb200_score_batch `impl`) */
 enum {
   NEMB200_SCORE_AUTO = 0,    /* tensor-core path, best epilogue for the dataset */
@@ -170,6 +176,8 @@ int nemb200_order_to_graph(const int32_t *d_orders, int n_chains, int S, int rul
  *      fit on the GPU at once) and the CUDA-graph loop around the tensor-core score otherwise.
  *      d_workspace: nemb200_mcmc_workspace_bytes(h, n_chains) bytes. */
 size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_chains);
+/* the same for one specific `rule`: NEMB200_RULE_FIT needs two (S+1) x E float64 tables and five S x S matrices per chain */
+size_t nemb200_mcmc_workspace_bytes_rule(const nemb200_dataset *h, int n_chains, int rule);
 int nemb200_mcmc_run(const nemb200_dataset *h, int n_chains, int64_t n_iters, int64_t iter0,
                      int64_t burn_in, const double *d_gamma, double swap_prob, uint64_t seed,
                      uint32_t chain_offset, int rule, const uint32_t *d_cand_bits, int use_nem,

@@ -13,6 +13,9 @@ constexpr int kCellRows = 48;
 __global__ void __launch_bounds__(128) k_cell_ratios(const uint32_t *__restrict__ dcol, int S, int W, int E, double A, double B,
                                                      const double *__restrict__ weights, int apply_expit,
                                                      double *__restrict__ cell) {
+  // blockIdx.z: chain of a batch (the device-resident fit loop): S x S weights and (S+1) x E cell ratios per chain
+  weights += (size_t)blockIdx.z * S * S;
+  cell += (size_t)blockIdx.z * (S + 1) * E;
   extern __shared__ double sh[];  // l0[rows*S], l1[rows*S]
   const int i_lo = blockIdx.y * kCellRows, i_hi = min(S, i_lo + kCellRows), rows = i_hi - i_lo;
   double *l0 = sh, *l1 = sh + rows * S;
@@ -44,6 +47,9 @@ __global__ void __launch_bounds__(128) k_cell_ratios(const uint32_t *__restrict_
 // per-column logaddexp.reduce over `rows` rows, optional posterior weights exp(cell - colsum), block partial sums
 __global__ void __launch_bounds__(256) k_cell_ll(const double *__restrict__ cell, int rows, int E, double *__restrict__ ow,
                                                  double *__restrict__ partial) {
+  cell += (size_t)blockIdx.y * rows * E;                    // blockIdx.y: chain of a batch
+  if (ow != nullptr) ow += (size_t)blockIdx.y * rows * E;
+  partial += (size_t)blockIdx.y * gridDim.x;
   __shared__ double red[256];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   double cs = 0.0;
@@ -65,11 +71,11 @@ __global__ void __launch_bounds__(256) k_cell_ll(const double *__restrict__ cell
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
-__global__ void k_sum_partials(const double *partial, int n, double *out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+__global__ void k_sum_partials(const double *partial, int n, double *out) {  // blockIdx.x: chain of a batch
+  if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s += partial[i];
-    *out = s;
+    for (int i = 0; i < n; ++i) s += partial[(size_t)blockIdx.x * n + i];
+    out[blockIdx.x] = s;
   }
 }
 
@@ -186,6 +192,10 @@ __global__ void __launch_bounds__(kFitThreads) k_fit_edges(const uint32_t *__res
                                                            const double *__restrict__ ow, const double *__restrict__ anc_x,
                                                            const uint8_t *__restrict__ mask, double *__restrict__ out) {
   __shared__ double red[kFitThreads];
+  {  // blockIdx.y: chain of a batch
+    const size_t c = blockIdx.y;
+    weights += c * S * S; anc_x += c * S * S; mask += c * S * S; out += c * S * S; ow += c * (size_t)(S + 1) * E;
+  }
   const int pr = blockIdx.x, k = pr % S;
   if (!mask[pr]) {
     if (threadIdx.x == 0) out[pr] = weights[pr];
@@ -245,6 +255,7 @@ __global__ void __launch_bounds__(kInvThreads) k_ancestor_x(const double *__rest
   __shared__ double red_v[kInvThreads];
   __shared__ int red_i[kInvThreads];
   const int tid = threadIdx.x;
+  weights += (size_t)blockIdx.x * S * S; perm += (size_t)blockIdx.x * S * S; out += (size_t)blockIdx.x * S * S;  // chain of a batch
   for (int i = tid; i < S * S; i += kInvThreads) {
     const double w = weights[i];
     const double e = perm[i] ? 1.0 / (1.0 + exp(-w)) : w;  // expit on the permissible parents only (:152-157)
@@ -309,6 +320,102 @@ extern "C" int nemb200_fit_edges(const nemb200_dataset *h, const double *d_weigh
   NEMB_REQUIRE(h && d_weights && d_order_weights && d_ancestor_x && d_mask && d_out_weights, "null argument");
   k_fit_edges<<<h->S * h->S, kFitThreads, 0, (cudaStream_t)stream>>>(h->dcol, h->S, h->W, h->E, h->A, h->B, d_weights,
                                                                     d_order_weights, d_ancestor_x, d_mask, d_out_weights);
+  NEMB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ---- the reference's order -> DAG step inside the device-resident loop (`rule = NEMB200_RULE_FIT`):
+//      what NEMOrderMCMC.method does between proposal and acceptance (nem_order_mcmc.py:276-286), for ALL chains of a
+//      batch at once and without a host round trip:
+//        reset: every permissible pair gets weight w0 (:50-77; all pairs)            k_fit_prep
+//        soft cell ratios of those weights, posterior attachment weights (:181-182)             k_cell_ratios, k_cell_ll
+//        ancestor_x = clip((I - expit W)^-1 - I, 0, 1) (:185)                                   k_ancestor_x
+//        one exact 1-D fit per permissible (node, parent) pair (:187-189, :160-170)            k_fit_edges
+//        threshold at 0.5 -> DAG (:210-214), closed if use_nem (:216-221)                       k_fit_threshold (+ closure)
+//        score of the thresholded graph through the same expit-on-weights cell ratios (:207)  k_fit_soft, k_cell_ratios, k_cell_ll
+//      In: prop_bits = the permissibility graph of each proposed order (edge a -> b iff a comes before b);
+//      out: prop_bits = the thresholded graph, prop_scores = its score.
+namespace {
+struct FitWs { uint8_t *perm; double *w, *cell, *ow, *anc, *fitted, *partial; int *sing; };
+size_t fit_carve(int S, int E, int n, void *base, FitWs *f) {
+  size_t off = 0;
+  uint8_t *b = (uint8_t *)base;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t ss = (size_t)n * S * S, ce = (size_t)n * (S + 1) * E;
+  const size_t o_perm = take(ss), o_w = take(8 * ss), o_cell = take(8 * ce), o_ow = take(8 * ce), o_anc = take(8 * ss),
+               o_fit = take(8 * ss), o_part = take(8 * (size_t)n * ((E + 255) / 256)), o_sing = take(16);
+  if (f) {
+    f->perm = b + o_perm; f->w = (double *)(b + o_w); f->cell = (double *)(b + o_cell); f->ow = (double *)(b + o_ow);
+    f->anc = (double *)(b + o_anc); f->fitted = (double *)(b + o_fit); f->partial = (double *)(b + o_part);
+    f->sing = (int *)(b + o_sing);
+  }
+  return off;
+}
+// perm[i][k] = 1 iff k is a permissible parent of i = edge k -> i of the permissibility graph; W[i][k] = w0 there
+__global__ void k_fit_prep(const uint32_t *__restrict__ bits, int S, int W, double w0, uint8_t *__restrict__ perm,
+                           double *__restrict__ w) {
+  const size_t c = blockIdx.x;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, k = idx - i * S;
+    const uint32_t on = (bits[(c * S + k) * W + (i >> 5)] >> (i & 31)) & 1u;
+    perm[c * S * S + idx] = (uint8_t)on;
+    w[c * S * S + idx] = on ? w0 : 0.0;
+  }
+}
+// fitted weights -> graph: edge k -> i iff W[i][k] > 0.5 (dag = dag_weights.T, :212-213)
+__global__ void k_fit_threshold(const double *__restrict__ fitted, const uint8_t *__restrict__ perm, int S, int W,
+                                uint32_t *__restrict__ bits) {
+  const size_t c = blockIdx.x;
+  for (int idx = threadIdx.x; idx < S * W; idx += blockDim.x) {
+    const int k = idx / W, wd = idx - k * W;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int i = wd * 32 + b;
+      if (i < S && perm[c * S * S + (size_t)i * S + k] && fitted[c * S * S + (size_t)i * S + k] > 0.5) m |= 1u << b;
+    }
+    bits[(c * S + k) * W + wd] = m;
+  }
+}
+// weights of the thresholded (and possibly closed) graph for the soft score: 1 on its edges, "0 but present" on the
+// other permissible pairs (the reference's loop over parents_list applies expit(0) = 0.5 to them), 0 elsewhere
+__global__ void k_fit_soft(const uint32_t *__restrict__ bits, const uint8_t *__restrict__ perm, int S, int W,
+                           double *__restrict__ w) {
+  const size_t c = blockIdx.x;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, k = idx - i * S;
+    const uint32_t on = (bits[(c * S + k) * W + (i >> 5)] >> (i & 31)) & 1u;
+    w[c * S * S + idx] = perm[c * S * S + idx] ? (on ? 1.0 : 1e-300) : 0.0;
+  }
+}
+}  // namespace
+
+size_t fit_pipeline_workspace_bytes(const nemb200_dataset *h, int n) { return fit_carve(h->S, h->E, n, nullptr, nullptr); }
+
+int launch_fit_pipeline(const nemb200_dataset *h, int n, uint32_t *prop_bits, double *prop_scores, void *ws, double w0,
+                        int use_nem, cudaStream_t st) {
+  const int S = h->S, W = h->W, E = h->E;
+  FitWs f;
+  fit_carve(S, E, n, ws, &f);
+  const int rows = S < kCellRows ? S : kCellRows;
+  const size_t smem_cell = sizeof(double) * 2 * rows * S, smem_inv = sizeof(double) * (size_t)S * S;
+  NEMB_CHECK_CUDA(cudaFuncSetAttribute(k_cell_ratios, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cell));
+  NEMB_CHECK_CUDA(cudaFuncSetAttribute(k_ancestor_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inv));
+  const dim3 gcell((E + 127) / 128, (S + kCellRows - 1) / kCellRows, n), gll((E + 255) / 256, n);
+  k_fit_prep<<<n, 256, 0, st>>>(prop_bits, S, W, w0, f.perm, f.w);
+  k_cell_ratios<<<gcell, 128, smem_cell, st>>>(h->dcol, S, W, E, h->A, h->B, f.w, 1, f.cell);
+  k_cell_ll<<<gll, 256, 0, st>>>(f.cell, S + 1, E, f.ow, f.partial);
+  k_ancestor_x<<<n, kInvThreads, smem_inv, st>>>(f.w, f.perm, S, f.anc, f.sing);
+  k_fit_edges<<<dim3(S * S, n), kFitThreads, 0, st>>>(h->dcol, S, W, E, h->A, h->B, f.w, f.ow, f.anc, f.perm, f.fitted);
+  k_fit_threshold<<<n, 128, 0, st>>>(f.fitted, f.perm, S, W, prop_bits);
+  if (use_nem) {
+    int rc = launch_closure(prop_bits, n, S, prop_bits, st);
+    if (rc) return rc;
+  }
+  k_fit_soft<<<n, 256, 0, st>>>(prop_bits, f.perm, S, W, f.w);
+  k_cell_ratios<<<gcell, 128, smem_cell, st>>>(h->dcol, S, W, E, h->A, h->B, f.w, 1, f.cell);
+  k_cell_ll<<<gll, 256, 0, st>>>(f.cell, S + 1, E, nullptr, f.partial);
+  k_sum_partials<<<n, 32, 0, st>>>(f.partial, (E + 255) / 256, prop_scores);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

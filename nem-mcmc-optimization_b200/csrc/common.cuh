@@ -96,6 +96,10 @@ size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair 
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
                     int impl, cudaStream_t st, int leave_sms_free = 0, int close = 0);
 
+size_t fit_pipeline_workspace_bytes(const nemb200_dataset *h, int n);
+int launch_fit_pipeline(const nemb200_dataset *h, int n, uint32_t *prop_bits, double *prop_scores, void *ws, double w0,
+                        int use_nem, cudaStream_t st);
+
 bool mcmc_fused_supported(const nemb200_dataset *h);
 bool mcmc_fused_preferred(const nemb200_dataset *h, int n_chains);
 int launch_mcmc_fused(const nemb200_dataset *h, int n, int64_t n_iters, int64_t iter0, int64_t burn_in, const double *d_gamma,

@@ -22,9 +22,10 @@ struct McmcWs {
   double *prop_scores;    // [n]
   void *score_ws;
   size_t score_ws_bytes;
+  void *fit_ws;           // NEMB200_RULE_FIT only: scratch of the per-order edge-weight fit (cell.cu: launch_fit_pipeline)
 };
 
-size_t carve(const nemb200_dataset *h, int n, void *base, McmcWs *w) {
+size_t carve(const nemb200_dataset *h, int n, void *base, McmcWs *w, bool fit = false) {
   size_t off = 0;
   uint8_t *b = (uint8_t *)base;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -33,7 +34,9 @@ size_t carve(const nemb200_dataset *h, int n, void *base, McmcWs *w) {
   size_t sws = score_tc_workspace_bytes(h, n, /*with_pair=*/true), wws = score_witness_workspace_bytes(n);  // chains are few: room for impl = PAIR
   if (wws > sws) sws = wws;
   size_t o_sw = take(sws);
+  size_t o_fit = fit ? take(fit_pipeline_workspace_bytes(h, n)) : 0;
   if (w) {
+    w->fit_ws = fit ? b + o_fit : nullptr;
     w->iter_a = (long long *)(b + o_iter); w->iter_b = w->iter_a + 1;
     w->since = (long long *)(b + o_since); w->prop_orders = (int32_t *)(b + o_po);
     w->prop_bits = (uint32_t *)(b + o_pb); w->prop_scores = (double *)(b + o_ps);
@@ -268,6 +271,12 @@ static int first_group_size(const nemb200_dataset *h, int n) {
   return ((n / 2 + G - 1) / G) * G;  // whole MMA N tiles in the first group
 }
 
+extern "C" size_t nemb200_mcmc_workspace_bytes_rule(const nemb200_dataset *h, int n_chains, int rule) {
+  if (!h || n_chains < 0) return 0;
+  if (rule != NEMB200_RULE_FIT) return nemb200_mcmc_workspace_bytes(h, n_chains);
+  return carve(h, n_chains, nullptr, nullptr, true);
+}
+
 extern "C" size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_chains) {
   if (!h || n_chains < 0) return 0;
   const int nA = first_group_size(h, n_chains);
@@ -332,8 +341,8 @@ extern "C" int nemb200_order_to_graph(const int32_t *d_orders, int n_chains, int
 }
 
 extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters, int64_t iter0, int64_t burn_in,
-                                const double *d_gamma, double swap_prob, uint64_t seed, uint32_t chain_offset, int rule,
-                                const uint32_t *d_cand_bits, int use_nem, int resume, int score_impl, int32_t *d_orders,
+                                const double *d_gamma, double swap_prob, uint64_t seed, uint32_t chain_offset, int rule_arg,
+                                const uint32_t *d_cand_bits, int use_nem_arg, int resume, int score_impl, int32_t *d_orders,
                                 double *d_curr_scores, uint32_t *d_curr_bits, double *d_best_scores, int32_t *d_best_orders,
                                 uint32_t *d_best_bits, int64_t *d_accept, uint32_t *d_edge_counts, double *d_score_trace,
                                 void *d_workspace, size_t workspace_bytes, void *stream) {
@@ -344,15 +353,18 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
   NEMB_REQUIRE(d_gamma && d_orders && d_curr_scores && d_curr_bits && d_best_scores && d_best_orders && d_best_bits &&
                    d_accept && d_workspace,
                "null device pointer");
-  NEMB_REQUIRE(rule == NEMB200_RULE_FULL || (rule == NEMB200_RULE_MASKED && d_cand_bits), "MASKED rule needs a candidate mask");
-  NEMB_REQUIRE(workspace_bytes >= nemb200_mcmc_workspace_bytes(h, n), "mcmc workspace too small");
+  const bool fit = rule_arg == NEMB200_RULE_FIT;
+  NEMB_REQUIRE(rule_arg == NEMB200_RULE_FULL || fit || (rule_arg == NEMB200_RULE_MASKED && d_cand_bits), "MASKED rule needs a candidate mask");
+  NEMB_REQUIRE(workspace_bytes >= nemb200_mcmc_workspace_bytes_rule(h, n, rule_arg),
+               fit ? "mcmc workspace too small for rule FIT: size it with nemb200_mcmc_workspace_bytes_rule" : "mcmc workspace too small");
   NEMB_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "mcmc workspace must be 256-byte aligned");
   NEMB_REQUIRE(swap_prob >= 0.0 && swap_prob <= 1.0, "swap_prob must be in [0,1]");
   cudaStream_t st = (cudaStream_t)stream;
   const int S = h->S, W = h->W;
   const unsigned long long sp = swap_prob >= 1.0 ? 0x100000000ull : (unsigned long long)(swap_prob * 4294967296.0 + 0.5);
-  if (score_impl == NEMB200_MCMC_FUSED || (score_impl == NEMB200_SCORE_AUTO && mcmc_fused_preferred(h, n)))
-    return launch_mcmc_fused(h, n, n_iters, iter0, burn_in, d_gamma, sp, seed, chain_offset, rule, d_cand_bits, use_nem,
+  NEMB_REQUIRE(!(fit && score_impl == NEMB200_MCMC_FUSED), "rule FIT runs in the kernel loop, not in the fused persistent kernel");
+  if (!fit && (score_impl == NEMB200_MCMC_FUSED || (score_impl == NEMB200_SCORE_AUTO && mcmc_fused_preferred(h, n))))
+    return launch_mcmc_fused(h, n, n_iters, iter0, burn_in, d_gamma, sp, seed, chain_offset, rule_arg, d_cand_bits, use_nem_arg,
                              resume, d_orders, d_curr_scores, d_curr_bits, d_best_scores, d_best_orders, d_best_bits,
                              d_accept, d_edge_counts, d_score_trace, st);
   constexpr int kUnroll = 16;  // iterations per captured CUDA graph
@@ -365,7 +377,7 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
   Group grp[2];
   int n_groups = 1;
   const int nA = first_group_size(h, n);
-  if (st != nullptr && nA < n && n_iters >= 2 * kUnroll) n_groups = 2;
+  if (st != nullptr && nA < n && n_iters >= 2 * kUnroll && !fit) n_groups = 2;
   if (n_groups == 2) {
     grp[0].c0 = 0; grp[0].n = nA; grp[1].c0 = nA; grp[1].n = n - nA;
     size_t off = carve(h, nA, d_workspace, &grp[0].w);
@@ -381,7 +393,7 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     }
   } else {
     grp[0].c0 = 0; grp[0].n = n;
-    carve(h, n, d_workspace, &grp[0].w);
+    carve(h, n, d_workspace, &grp[0].w, fit);
   }
 
   static const char *sms_env = getenv("NEMB200_SMS_FREE");  // tuning knob (diagnostics)
@@ -392,6 +404,9 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     const int grid = (g.n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int32_t *orders = d_orders + c0 * S;
     const uint32_t coff = chain_offset + (uint32_t)g.c0;
+    // rule FIT: the proposal kernel emits the permissibility graph of the proposed order (FULL rule, not closed -
+    // it is closed by construction); the fit pipeline turns it into the thresholded graph and its score
+    const int rule = fit ? NEMB200_RULE_FULL : rule_arg, use_nem = fit ? 0 : use_nem_arg;
     switch (W) {
       case 1: k_mcmc_propose<1><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
       case 2: k_mcmc_propose<2><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
@@ -399,8 +414,11 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
       default: k_mcmc_propose<4><<<grid, thr, 0, s>>>(orders, g.n, S, w.iter_a, w.iter_b, seed, coff, sp, rule, d_cand_bits, use_nem, init, w.prop_orders, w.prop_bits); break;
     }
     NEMB_CHECK_CUDA(cudaGetLastError());
-    int rc = score_dispatch(h, w.prop_bits, g.n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, s,
-                            n_groups == 2 ? sms_free : 0);
+    // (method() scores the start order with the constructor's weights, 1.0 on every permissible pair; every later
+    //  iteration resets them to 0.5: nem_order_mcmc.py:47, :57, :276)
+    int rc = fit ? launch_fit_pipeline(h, g.n, w.prop_bits, w.prop_scores, w.fit_ws, init ? 1.0 : 0.5, use_nem_arg, s)
+                 : score_dispatch(h, w.prop_bits, g.n, w.prop_scores, w.score_ws, w.score_ws_bytes, score_impl, s,
+                                  n_groups == 2 ? sms_free : 0);
     if (rc) return rc;
     // `n` (all chains) is the row stride of the score trace; every other array is passed at the group's offset
     k_mcmc_accept<<<g.n, kAcceptThreads, 0, s>>>(
@@ -429,8 +447,8 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     unsigned long long key = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
     mix((unsigned long long)n); mix(17ull + (unsigned long long)n_groups); mix((unsigned long long)burn_in); mix((unsigned long long)(uintptr_t)d_gamma);
-    mix(sp); mix(seed); mix(chain_offset); mix((unsigned long long)rule); mix((unsigned long long)(uintptr_t)d_cand_bits);
-    mix((unsigned long long)use_nem); mix((unsigned long long)score_impl); mix((unsigned long long)(uintptr_t)d_orders);
+    mix(sp); mix(seed); mix(chain_offset); mix((unsigned long long)rule_arg); mix((unsigned long long)(uintptr_t)d_cand_bits);
+    mix((unsigned long long)use_nem_arg); mix((unsigned long long)score_impl); mix((unsigned long long)(uintptr_t)d_orders);
     mix((unsigned long long)(uintptr_t)d_curr_scores); mix((unsigned long long)(uintptr_t)d_curr_bits);
     mix((unsigned long long)(uintptr_t)d_best_scores); mix((unsigned long long)(uintptr_t)d_best_orders);
     mix((unsigned long long)(uintptr_t)d_best_bits); mix((unsigned long long)(uintptr_t)d_accept);

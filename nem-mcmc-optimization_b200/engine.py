@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 
-RULE_FULL, RULE_MASKED = 0, 1
+RULE_FULL, RULE_MASKED, RULE_FIT = 0, 1, 2  # FIT: nemb200_mcmc_run only (the reference's per-order edge-weight fit)
 SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5, "pair": 6, "lutm": 7}
 
 
@@ -372,7 +372,7 @@ class ChainState:
         self.iters_done = 0
         self.started = False
         self.trace = None
-        need = _lib.lib().nemb200_mcmc_workspace_bytes(ds._h, n)
+        need = _lib.lib().nemb200_mcmc_workspace_bytes_rule(ds._h, n, int(rule))
         self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
         self._ws_off = (-self._ws.data_ptr()) % 256
         self._ws_bytes = need

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib, engine, utils
 
-_RULES = {"full": engine.RULE_FULL, "masked": engine.RULE_MASKED, 0: 0, 1: 1}
+_RULES = {"full": engine.RULE_FULL, "masked": engine.RULE_MASKED, "fit": engine.RULE_FIT, 0: 0, 1: 1, 2: 2}
 
 
 def start_orders(perm_order, n_chains, seed):
@@ -217,9 +217,12 @@ class NEMOrderMCMC:
         """nem_order_mcmc.py:257-310 -> (best_score, best_dag) with best_dag[j][i]=1 iff edge j->i.
         n_chains independent chains run at once (chain 0 starts from self.perm_order); the best over
         all chains is returned and `edge_freq` holds the posterior edge frequencies."""
-        if rule == "fit":
+        if rule == "fit_host":   # the host-driven single-chain loop (Python's `random`, one sync per iteration)
             return self._method_fit(swap_prob, gamma, seed, n_iterations, verbose, use_nem)
-        ds = getattr(self.nem, "score_dataset", self.nem.dataset)
+        # rule="fit": the reference's own order -> DAG step (per-order edge-weight fit + threshold, :276-286) inside the
+        # device-resident loop, for all n_chains chains at once (NEMB200_RULE_FIT); the general-weight kernels index
+        # E-genes as stored in the plain dataset
+        ds = self.nem.dataset if rule in ("fit", 2) else getattr(self.nem, "score_dataset", self.nem.dataset)
         orders0 = start_orders(self.perm_order, n_chains, seed)
         gam = np.broadcast_to(np.asarray(gamma, dtype=np.float64), (n_chains,))
         state = engine.ChainState(ds, orders0, gam, edge_counts=True, seed=seed, rule=_RULES[rule], cand=cand,

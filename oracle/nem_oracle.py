@@ -341,6 +341,72 @@ def mcmc_chain(D, A, B, order0, n_iter, gamma, swap_prob=0.95, seed=1234, chain=
                 curr_score_list=curr_scores, edge_counts=edge_counts)
 
 
+def soft_score(W, D, A, B, perm):
+    """utils.compute_ll(compute_cell_ratios(W)) as the MCMC driver calls it (nem_order_mcmc.py:207, :79-87):
+    expit is applied to EVERY permissible pair's weight, also to the zeros of a thresholded graph (expit(0) = 0.5)."""
+    s = np.asarray(D).shape[0]
+    T, _, U = score_tables(D, A, B)
+    cell = U.copy()
+    for i in range(s):
+        for k in range(s):
+            if perm[i][k]:
+                w = _expit(W[i][k])
+                cell[i] += np.log(1.0 - w + w * np.exp(T[k]))
+    return float(np.sum(np.logaddexp.reduce(cell, axis=0)))
+
+
+RULE_FIT = 2  # order -> DAG as the reference does it: per-order edge-weight fit + threshold (SURVEY 8 f-1)
+
+
+def fit_order_to_graph(D, A, B, order, w0, use_nem):
+    """What NEMOrderMCMC.method does between proposal and acceptance (nem_order_mcmc.py:276-286), with the exact
+    minimiser: reset every permissible weight to w0 (:50-77, all pairs - SURVEY Q7), one pass of the per-edge fits
+    (get_optimal_weights(init=True, max_iter=1), :172-208), threshold at 0.5 (create_dag :210-214; create_nem closes it,
+    :216-221), score the thresholded graph through the driver's expit-on-weights cell ratios (:207).
+    Returns (graph with [k][i] = 1 iff edge k -> i, score)."""
+    s = np.asarray(D).shape[0]
+    order = np.asarray(order)
+    pos = np.empty(s, dtype=int)
+    pos[order] = np.arange(s)
+    perm = pos[None, :] < pos[:, None]
+    W = np.where(perm, w0, 0.0)
+    new, _ = fit_pass(D, A, B, order, W, "exact")
+    wbin = (new > 0.5).astype(np.int64) * perm
+    if use_nem:
+        wbin = closure_bool(wbin)
+    return wbin.T.copy(), soft_score(wbin.astype(np.float64), D, A, B, perm)
+
+
+def mcmc_chain_fit(D, A, B, order0, n_iter, gamma, swap_prob=0.95, seed=1234, chain=0, use_nem=False, iter0=0):
+    """mcmc_chain with the reference's order -> DAG step (rule FIT): the start order is scored from the constructor's
+    weights (1.0 on every permissible pair, nem_order_mcmc.py:47 + :258), every proposal from weights reset to 0.5
+    (:57, :276).  Same Philox draws and accept rule as mcmc_chain."""
+    s = D.shape[0]
+    sp = swap_prob_to_u32(swap_prob)
+    k0, k1 = seed & _M32, (seed >> 32) & _M32
+    curr_order = np.array(order0, dtype=np.int64)
+    curr_g, curr = fit_order_to_graph(D, A, B, curr_order, 1.0, use_nem)
+    best, best_order, best_g = curr, curr_order.copy(), curr_g.copy()
+    n_acc, all_scores = 0, [curr]
+    edge_counts = np.zeros((s, s), dtype=np.int64)
+    for t in range(iter0, iter0 + n_iter):
+        r = philox4x32_10(t & _M32, (t >> 32) & _M32, chain & _M32, 0, k0, k1)
+        cand_order = propose(curr_order, r, sp)
+        g, ll = fit_order_to_graph(D, A, B, cand_order, 0.5, use_nem)
+        all_scores.append(ll)
+        u = (r[3] + 0.5) / 4294967296.0
+        with np.errstate(over="ignore"):
+            rate = np.exp(gamma * (ll - curr))
+        if u < rate:
+            n_acc += 1
+            curr, curr_order, curr_g = ll, cand_order, g
+            if curr > best:
+                best, best_order, best_g = curr, curr_order.copy(), curr_g.copy()
+        edge_counts += curr_g
+    return dict(best_score=best, best_order=best_order, best_graph=best_g, curr_score=curr, curr_order=curr_order,
+                n_accept=n_acc, all_score_list=all_scores, edge_counts=edge_counts)
+
+
 # --------------------------------------------------------------------------
 # replica exchange (nem_order_mcmc.py:316-363)
 # --------------------------------------------------------------------------

@@ -970,14 +970,45 @@ def test_mcmc_method_with_fitted_weights(nb):
     end_nodes = np.array([0, 1, 2, 3, 4, 0, 1, 2])
     model = nb.NEM(adj, end_nodes, (0.05, 0.1), 5, 8, seed=42)
     mc = nb.NEMOrderMCMC(model, np.array([4, 3, 2, 1, 0]))
-    best_score, best_dag = mc.method(n_iterations=110, gamma=2 * 5 / 8, seed=42, verbose=False, rule="fit")
-    assert best_dag.shape == (5, 5) and set(np.unique(best_dag)) <= {0, 1}
-    assert len(mc.all_score_list) == 111 and len(mc.curr_score_list) == 111
-    assert best_score == max(mc.best_score_list) and best_score >= mc.all_score_list[0]
-    assert sorted(mc.best_order.tolist()) == [0, 1, 2, 3, 4]
-    pos = np.empty(5, dtype=int); pos[mc.best_order] = np.arange(5)
-    a, b = np.nonzero(best_dag)
-    assert np.all(pos[a] < pos[b])           # only order-compatible edges (SURVEY Q7 fixed)
+    for rule in ("fit_host", "fit"):         # the host-driven loop and the device-resident loop (NEMB200_RULE_FIT)
+        mc = nb.NEMOrderMCMC(model, np.array([4, 3, 2, 1, 0]))
+        best_score, best_dag = mc.method(n_iterations=110, gamma=2 * 5 / 8, seed=42, verbose=False, rule=rule)
+        assert best_dag.shape == (5, 5) and set(np.unique(best_dag)) <= {0, 1}
+        assert len(mc.all_score_list) == 111 and len(mc.curr_score_list) == 111
+        assert best_score == max(mc.best_score_list) and best_score >= mc.all_score_list[0]
+        assert sorted(mc.best_order.tolist()) == [0, 1, 2, 3, 4]
+        pos = np.empty(5, dtype=int); pos[mc.best_order] = np.arange(5)
+        a, b = np.nonzero(best_dag)
+        assert np.all(pos[a] < pos[b])       # only order-compatible edges (SURVEY Q7 fixed)
+
+
+@pytest.mark.parametrize("S,E,use_nem", [(6, 40, False), (9, 80, True), (13, 126, False)])
+def test_mcmc_fit_rule_device_loop_vs_oracle(nb, S, E, use_nem):
+    """rule FIT inside the device-resident loop (nemb200_mcmc_run, NEMB200_RULE_FIT): per iteration and chain the
+    reference's reset -> edge-weight fits -> threshold (-> closure) -> soft score (nem_order_mcmc.py:276-286, :172-208)
+    with no host round trip.  Accept decisions, orders, thresholded graphs, scores and edge counts equal the oracle
+    chain that restates the same steps with the exact minimiser and the same Philox stream."""
+    _, _, D = orc.synth_dataset(S, E, seed=S + 3)
+    A, B = orc.nem_constants(0.05, 0.1)
+    rng = np.random.default_rng(S)
+    n_chains, n_iter = 5, 24
+    gamma = 2.0 * S / E
+    orders0 = np.stack([rng.permutation(S) for _ in range(n_chains)]).astype(np.int32)
+    ds = nb.Dataset(D, A, B)
+    st = nb.ChainState(ds, orders0, gamma, edge_counts=True, seed=31, chain_offset=2, rule=nb.RULE_FIT, use_nem=use_nem)
+    st.run(n_iter, swap_prob=0.9, trace=True)
+    res = st.result()
+    per_chain = st.edge_counts.cpu().numpy().astype(np.int64).reshape(n_chains, S, S)
+    for c in range(n_chains):
+        ref = orc.mcmc_chain_fit(D, A, B, orders0[c], n_iter, gamma, swap_prob=0.9, seed=31, chain=2 + c, use_nem=use_nem)
+        assert np.allclose(res.score_trace[:, 0, c], ref["all_score_list"][1:], rtol=1e-9), c
+        _compare_chain(res, c, ref, S, tol=1e-9)
+        assert np.array_equal(per_chain[c], ref["edge_counts"])
+    assert 0 < res.accept_counts.sum() < n_chains * n_iter
+    # resume == single run
+    st2 = nb.ChainState(ds, orders0, gamma, edge_counts=True, seed=31, chain_offset=2, rule=nb.RULE_FIT, use_nem=use_nem)
+    st2.run(10, swap_prob=0.9); st2.run(n_iter - 10, swap_prob=0.9)
+    assert torch.equal(st2.orders, st.orders) and torch.equal(st2.accept, st.accept)
 
 
 def test_score_stream_pipelined_host_batches(nb):
