@@ -1249,6 +1249,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
 // warp per graph) pairs sites greedily in order of ancestor count, keeps the S - 32 cheapest pairs (tables of
 // at most kPairLim entries, kPairCap per graph) and leaves the other sites single: a 50-site graph becomes 32
 // accumulator columns.  Graphs that cannot be planned are appended to a list and scored by the one-site kernel.
+constexpr int kPlanWindow = 8;     // partner window in sorted order (<= 32)
 constexpr int kPlanThreads = 256;  // one CTA per graph; the planner is latency-bound, so phases are spread over many threads
 __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__restrict__ phi, int n, int S, int W,
                                                            const float *__restrict__ tabs, uint8_t *__restrict__ plan,
@@ -1269,24 +1270,26 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
   for (int i = tid; i < (S + 1) * (S + 2) / 2; i += kPlanThreads) s_tab[i] = tabs[i];
   __syncthreads();
   PTRACE(1);
-  // ancestor-or-self masks (columns of I | Phi): thread (site j, quarter qr) builds 16 bits = rows 16qr .. 16qr+15
-  {
-    const int j = tid & 63, qr = tid >> 6;
-    uint32_t m = 0;
-    if (j < S) {
-      const int a_end = min(S, 16 * qr + 16);
-      for (int a = 16 * qr; a < a_end; ++a) {
-        const uint32_t bit = ((s_rows[a * W + (j >> 5)] >> (j & 31)) & 1u) | (a == j ? 1u : 0u);
-        m |= bit << (a & 15);
+  // ancestor-or-self masks (columns of I | Phi) by 32 x 32 bit-block transposes (five shuffle-xor butterfly steps each,
+  // like the score kernel's operand expansion): warp w < 2 transposes the two row blocks of column block w, lane l then
+  // holds the mask of site 32 w + l.  (33 <= S <= 52: two words per row.)
+  if (warp < 2) {
+    uint32_t x[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      uint32_t v = (t * 32 + lane < S) ? s_rows[(t * 32 + lane) * W + warp] : 0u;
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        const uint32_t m = sft == 16 ? 0x0000FFFFu : (sft == 8 ? 0x00FF00FFu : (sft == 4 ? 0x0F0F0F0Fu : (sft == 2 ? 0x33333333u : 0x55555555u)));
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, v, sft);
+        v = (lane & sft) ? ((v & ~m) | ((y >> sft) & m)) : ((v & m) | ((y << sft) & ~m));
       }
+      x[t] = v;
     }
-    reinterpret_cast<uint16_t *>(&s_site[j])[qr] = (uint16_t)m;
-    if (qr == 0) s_sorted[j] = make_uint4(0u, 0u, 1u << 20, 255u);
-  }
-  __syncthreads();
-  if (tid < 64) {
-    const uint4 v = s_site[tid];
-    s_site[tid] = make_uint4(v.x, v.y, tid < S ? (uint32_t)(__popc(v.x) + __popc(v.y)) : (1u << 20), (uint32_t)tid);
+    const int j = warp * 32 + lane;
+    x[warp] |= 1u << lane;  // the site itself
+    s_site[j] = make_uint4(j < S ? x[0] : 0u, j < S ? x[1] : 0u, j < S ? (uint32_t)(__popc(x[0]) + __popc(x[1])) : (1u << 20), (uint32_t)j);
+    s_sorted[j] = make_uint4(0u, 0u, 1u << 20, 255u);
   }
   __syncthreads();
   PTRACE(2);
@@ -1300,12 +1303,14 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
   }
   __syncthreads();
   PTRACE(3);
-  // all pair costs inside the window, in parallel: thread (a, wq) takes partners a+1+wq, a+1+wq+4, ..
+  // all pair costs inside the window, in parallel: thread (a, wq) takes partners a+1+wq, a+1+wq+4.  The window is the
+  // next kPlanWindow sites in sorted order (measured on the benchmark's graph families: 8 finds as many cheap pairs
+  // as 32 - no graph falls back - at a quarter of the evaluations)
   {
     const int a = tid >> 2, wq = tid & 3;
     const uint4 si = s_sorted[a];
 #pragma unroll
-    for (int w = wq; w < 32; w += 4) {
+    for (int w = wq; w < kPlanWindow; w += 4) {
       const int idx = a + 1 + w;
       uint32_t cost = 0xFFFFu;
       if (a < S && idx < S) {
@@ -1331,7 +1336,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
       if (a >= S - 1) break;
       if (a < 32) u0 |= 1u << a; else u1 |= 1u << (a - 32);  // paired below or left single
       const int idx = a + 1 + lane;
-      const uint32_t c = s_cost[a][lane];
+      const uint32_t c = lane < kPlanWindow ? s_cost[a][lane] : 0xFFFFu;
       const bool taken = idx >= 64 || ((((idx < 32 ? u0 : u1) >> (idx & 31)) & 1u) != 0u);
       const uint32_t packed = (c == 0xFFFFu || taken) ? 0xFFFFFFFFu : ((c << 8) | (uint32_t)lane);
       const uint32_t best = __reduce_min_sync(0xffffffffu, packed);
@@ -1413,7 +1418,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
     const uint32_t total_g = __shfl_sync(0xffffffffu, incl, 31);
     dst[4] = make_uint4((uint32_t)kind | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16) | ((uint32_t)nC << 24),
                         (uint32_t)d1 | ((uint32_t)d2 << 8) | (toff << 16), total_g, 0u);
-    s_col[lane] = make_uint4((uint32_t)kind, (uint32_t)n1 | ((uint32_t)n2 << 8) | ((uint32_t)nC << 16), toff, 0u);
+    s_col[lane] = make_uint4((uint32_t)kind, (uint32_t)n1 | ((uint32_t)n2 << 8) | ((uint32_t)nC << 16), toff, tsz);
   }
   __syncthreads();
   PTRACE(7);
