@@ -50,7 +50,12 @@ enum {
   NEMB200_SCORE_TC_EX2_2PASS = 4, /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
   NEMB200_MCMC_FUSED = 5, /* nemb200_mcmc_run only: persistent one-CTA-per-chain kernel (small S*E) */
   NEMB200_SCORE_TC_PAIR = 6, /* tcgen05 GEMM + pair-merged table epilogue: two attachment sites per look-up (33 <= S <= 52) */
-  NEMB200_SCORE_TC_LUTM = 7  /* tcgen05 GEMM + multi-level exp-table epilogue: dynamic ranges of up to ~630 binary orders, 16 <= S <= 125 */
+  NEMB200_SCORE_TC_LUTM = 7, /* tcgen05 GEMM + multi-level exp-table epilogue: dynamic ranges of up to ~630 binary orders, 16 <= S <= 125 */
+  NEMB200_SCORE_TC_LUT_MIX = 8 /* NEMB200_SCORE_TC_LUT with every fourth group of four attachment sites through ex2.approx
+                                  instead of the table (the look-ups bound the kernel on the shared-memory pipe, the MUFU
+                                  pipe is idle): about 5 % faster, relative error of a score <= 5e-7 instead of <= 5e-8.
+                                  Column stride 50 (S = 50) only.  AUTO picks it in nemb200_score_batch and
+                                  nemb200_closure_score_batch; nemb200_mcmc_run's AUTO stays with the table-only kernel. */
 };
 
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */

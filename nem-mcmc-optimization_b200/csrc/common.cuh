@@ -93,6 +93,7 @@ size_t score_witness_workspace_bytes(int n);
 int launch_score_witness(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws,
                          cudaStream_t st);
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair = false);
+bool score_tc_has_mix(const nemb200_dataset *h);  // NEMB200_SCORE_TC_LUT_MIX available for this dataset
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
                     int impl, cudaStream_t st, int leave_sms_free = 0, int close = 0);
 

@@ -307,6 +307,7 @@ extern "C" int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_p
                                    void *d_workspace, size_t workspace_bytes, int impl, void *stream) {
   NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
   NEMB_REQUIRE(n_graphs == 0 || (d_phi_bits && d_scores && d_workspace), "null device pointer");
+  if (impl == NEMB200_SCORE_AUTO && h->S >= 8 && score_tc_has_mix(h)) impl = NEMB200_SCORE_TC_LUT_MIX;  // sweeps only (see nemb200.h)
   return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream);
 }
 
@@ -316,6 +317,7 @@ extern "C" int nemb200_closure_score_batch(const nemb200_dataset *h, const uint3
   NEMB_REQUIRE(n_graphs == 0 || (d_adj_bits && d_scores && d_workspace), "null device pointer");
   NEMB_REQUIRE(impl != NEMB200_SCORE_WITNESS && impl != NEMB200_SCORE_TC_PAIR && h->S >= 8,
                "closure + score in one launch needs a tensor-core score kernel other than the pair-merged one (S >= 8)");
+  if (impl == NEMB200_SCORE_AUTO && score_tc_has_mix(h)) impl = NEMB200_SCORE_TC_LUT_MIX;
   return launch_score_tc(h, d_adj_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, 1);
 }
 

@@ -475,6 +475,7 @@ __device__ __forceinline__ void tile_epilogue_generic(uint32_t taddr, const floa
 // float4 of biases) - otherwise the LSU and MUFU pipes would be used one after the other, not together.
 // NLUT >= S_T: table only.  Otherwise NLUT is a period P: of every P groups of four sites the last one is an ex2 group
 // (a fraction 1/P of the sites leaves the LSU pipe for the MUFU pipe).
+constexpr int kMixPeriod = 4;  // the shipped mix (measured at S=50, E=10k, 1024 graphs: P=3 90.1 us, 4 87.1, 5 87.3, table only 92.0)
 template <int S_T, int NLUT>
 __host__ __device__ constexpr bool is_lut_site(int j) { return NLUT >= S_T ? true : ((j >> 2) % NLUT) != NLUT - 1; }
 // int -> float without I2F (I2F and ex2 share the XU pipe): for 0 <= a < 2^14, (a << 9) + 0x46800000 is the bit pattern
@@ -637,9 +638,17 @@ __device__ __forceinline__ void pin_regs(float (&v)[N]) {
   }
 }
 
-template <int S_T, int C0, int C1, int SHIFT>
+// number of ex2 sites per graph of a mixed instantiation (NLUT < S_T: of every NLUT groups of four sites the last one), and
+// the rank of site j among them
+template <int S_T, int NLUT>
+__host__ __device__ constexpr int n_ex2_sites() { int n = 0; for (int j = 0; j < S_T; ++j) n += is_lut_site<S_T, NLUT>(j) ? 0 : 1; return n; }
+template <int S_T, int NLUT>
+__host__ __device__ constexpr int ex2_rank(int j) { int n = 0; for (int q = 0; q < j; ++q) n += is_lut_site<S_T, NLUT>(q) ? 0 : 1; return n; }
+
+template <int S_T, int NLUT, int C0, int C1, int SHIFT, int NB>
 __device__ __forceinline__ void lean_cols(const uint32_t (&r)[32], float null_term, float cexp, bool ok_tile, int ng_mine,
-                                          uint64_t &a0, uint64_t &a1, LeanPending &pd, double (&part)[kMaxG / 4]) {
+                                          uint64_t &a0, uint64_t &a1, LeanPending &pd, double (&part)[kMaxG / 4],
+                                          const float (&bq)[NB], float k1) {
   static_assert(S_T % 2 == 0 && C0 % 2 == 0 && C1 % 2 == 0, "column pairs must not straddle graphs or chunks");
   if constexpr (C1 > C0) {
     float v[C1 - C0];
@@ -648,6 +657,8 @@ __device__ __forceinline__ void lean_cols(const uint32_t (&r)[32], float null_te
       constexpr int kMixP = (NEMB200_EXP & 128) ? 4 : ((NEMB200_EXP & 256) ? 3 : ((NEMB200_EXP & 512) ? 2 : 0));  // timing probe: 1/P of the pairs through ex2 (wrong bias)
       const int jj = (C0 + i) % S_T;
       if (kMixP > 0 && ((jj >> 1) % kMixP) == kMixP - 1) v[i] = ex2f(fmaf(__uint_as_float((r[i + SHIFT] << 9) + kMagic14), -1e-4f, 1.0f));
+      else if (!is_lut_site<S_T, NLUT>(jj))  // mixed instantiation: this site goes through the MUFU pipe (x = k1 * acc + bias_j)
+        v[i] = ex2f(fmaf(__uint_as_float((r[i + SHIFT] << 9) + kMagic14), k1, bq[ex2_rank<S_T, NLUT>(jj) < NB ? ex2_rank<S_T, NLUT>(jj) : 0]));
       else v[i] = (NEMB200_EXP & 1) ? __uint_as_float((r[i + SHIFT] & 0xFFFFu) | 0x3F800000u) : lds_f32(r[i + SHIFT]);
     }
     if constexpr ((NEMB200_EXP & 1024) != 0) {  // sensitivity probe: every look-up issued twice
@@ -679,9 +690,9 @@ __device__ __forceinline__ void lean_cols(const uint32_t (&r)[32], float null_te
   }
 }
 
-template <int S_T>
-__device__ __forceinline__ void item_tiles_lean(const Params &p, uint32_t tmem_cols, int ng_mine, int row0, int nt, uint32_t it0,
-                                                uint32_t bar_tfull, uint32_t bar_tempty, double (&part)[kMaxG / 4]) {
+template <int S_T, int NLUT>
+__device__ __forceinline__ void item_tiles_lean(const Params &p, uint32_t tmem_cols, const float *sBias, int ng_mine, int row0, int nt,
+                                                uint32_t it0, uint32_t bar_tfull, uint32_t bar_tempty, double (&part)[kMaxG / 4]) {
   constexpr int G = tile_graphs(S_T);
   constexpr int NCOL = (G / epi_warpgroups(S_T)) * S_T;
   // chunk A = columns [0, NA), chunk B = [NA, NCOL): two TMEM loads of up to 32 columns per tile, each issued one
@@ -700,6 +711,17 @@ __device__ __forceinline__ void item_tiles_lean(const Params &p, uint32_t tmem_c
   uint32_t ra[32], rb[32];
   uint64_t a0 = 0, a1 = 0;
   LeanPending pd = {1.f, 0, false};
+  // mixed instantiation (one graph per warpgroup): the biases of the graph's ex2 sites stay in registers for the item
+  constexpr int NBQ = NLUT < S_T ? n_ex2_sites<S_T, NLUT>() : 1;
+  static_assert(NLUT >= S_T || NCOL == S_T, "the ex2 mix is written for one graph per warpgroup");
+  float bq[NBQ];
+  bq[0] = 0.f;
+  if constexpr (NLUT < S_T) {
+#pragma unroll
+    for (int j = 0; j < S_T; ++j)
+      if (!is_lut_site<S_T, NLUT>(j)) bq[ex2_rank<S_T, NLUT>(j)] = sBias[j];
+  }
+  const float k1 = p.k1;
   uint32_t ph = (it0 >> 1) & 1u;  // parity of the t_full barriers for the current PAIR of tiles
   // one tile out of accumulator buffer BUF; `more`: another tile follows (its chunk A is fetched before chunk B is used)
   auto tile = [&](auto buf_c, int t, bool more) {
@@ -708,19 +730,19 @@ __device__ __forceinline__ void item_tiles_lean(const Params &p, uint32_t tmem_c
     tmem_wait_ld();  // A(t) is in registers
     if constexpr (NB > 0) { if (!(NEMB200_EXP & 2)) TMEM_LDN(NB, tcols + BUF * 256u + (uint32_t)BSTART, rb); }
     if constexpr (NB > 0 && (NEMB200_EXP & 2048) != 0) TMEM_LDN(NB, tcols + BUF * 256u + (uint32_t)BSTART, rb);  // sensitivity probe: twice the TMEM loads
-    lean_cols<S_T, 0, NA1, 0>(ra, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
+    lean_cols<S_T, NLUT, 0, NA1, 0>(ra, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part, bq, k1);
     if constexpr (NB > 0) tmem_wait_ld();  // B(t) is in registers: this warp no longer needs the accumulator buffer
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bempty + 8 * BUF);
-    lean_cols<S_T, NA1, NA, NA1>(ra, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
+    lean_cols<S_T, NLUT, NA1, NA, NA1>(ra, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part, bq, k1);
     if (more) {
       mbar_wait(bfull + 8 * (BUF ^ 1u), BUF ? (ph ^ 1u) : ph);
       tc_fence_after();
       if (!(NEMB200_EXP & 2)) TMEM_LDN(NAL, tcols + (BUF ^ 1u) * 256u, ra);  // lands while chunk B is being looked up
       if constexpr ((NEMB200_EXP & 2048) != 0) TMEM_LDN(NAL, tcols + (BUF ^ 1u) * 256u, ra);
     }
-    if constexpr (NB > 0) lean_cols<S_T, NA, NCOL, BSH>(rb, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part);
+    if constexpr (NB > 0) lean_cols<S_T, NLUT, NA, NCOL, BSH>(rb, null_term, cexp, ok_tile, ng_mine, a0, a1, pd, part, bq, k1);
   };
   int t = 0;
   if (it0 & 1u) {  // the item starts on buffer 1
@@ -975,6 +997,13 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     }
   }
 
+  constexpr bool kRegSplit = S_T > 0 && NLUT < S_T && !PAIR;
+  if (warp < 4) {
+  if constexpr (kRegSplit) {
+    // the mixed epilogue keeps its ex2 biases in registers: the four non-epilogue warps (one warpgroup: they meet here
+    // after the prologue expansion) give registers to the sixteen epilogue warps (CTA pool: 128 x 32 released = 4 x 128 x 8 taken)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  }
   if (warp == 0) {
     // =============================== TMA producer: A tiles of every item, in order ===================
     // The whole warp walks the loop (uniform control flow: addresses and barrier parities stay in uniform
@@ -1106,8 +1135,10 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       }
       asm volatile("bar.sync 6, 64;" ::: "memory");  // sRows is reused by the next item
     }
+  }
   } else {
     // =============================== epilogue: 4 warpgroups share every tile, a quarter of its graphs each ===
+    if constexpr (kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int wg = (warp - 4) >> 2, quarter = warp & 3, tw = threadIdx.x - 128 - wg * 128;
     const int gq = G >= NWG ? G / NWG : 1;                       // graphs per warpgroup (G == 2: warpgroups 2,3 idle)
     const bool split = EPI == EPI_LUTM && G == 2;                // ... unless two warpgroups share a graph (tile_epilogue_split)
@@ -1132,9 +1163,9 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
 #pragma unroll
       for (int g = 0; g < kMaxG / 4; ++g) part[g] = 0.0;
       if (S_T > 0 && ng_mine > 0) {
-        if constexpr (S_T > 0 && NLUT >= S_T && S_T % 2 == 0 && !NEMB200_OLD_EPILOGUE)
-          item_tiles_lean<S_T>(p, tmem_base + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16), ng_mine,
-                               m0 * 128 + quarter * 32 + lane, nt, it, bar_tfull, bar_tempty, part);
+        if constexpr (S_T > 0 && S_T % 2 == 0 && !NEMB200_OLD_EPILOGUE)
+          item_tiles_lean<S_T, NLUT>(p, tmem_base + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16), bias, ng_mine,
+                                     m0 * 128 + quarter * 32 + lane, nt, it, bar_tfull, bar_tempty, part);
         else if constexpr (S_T > 0)
           item_tiles_static<S_T, NLUT>(p, tmem_base + (uint32_t)(gl * p.CS) + ((uint32_t)(quarter * 32) << 16), bias, ng_mine,
                                        m0 * 128 + quarter * 32 + lane, nt, it, bar_tfull, bar_tempty, part);
@@ -1480,7 +1511,7 @@ int launch_kernel(K kern, const Params &p, int grid, int threads, cudaStream_t s
 }
 
 // the specialised one-site table kernel for the dataset's column stride
-int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t st) {
+int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t st, bool mix = false) {
   // the dataset fixed the column stride: S itself for the four headline shapes, S rounded up to 8 otherwise
   switch (h->CS == h->S ? h->S : -h->CS) {
 #ifndef NEMB200_DEV_S50  // (development builds compile the S=50 instantiations only)
@@ -1488,15 +1519,10 @@ int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t
     case 20: return launch_kernel(k_score_tc<EPI_LUT, 20, 20>, p, grid, cta_threads(20), st);
     case 30: return launch_kernel(k_score_tc<EPI_LUT, 30, 30>, p, grid, cta_threads(30), st);
 #endif
-    case 50: {
-      static const char *mix_env = getenv("NEMB200_MIX");  // diagnostics: 1/P of the sites through ex2.approx
-      const int mix = mix_env ? atoi(mix_env) : 0;
-      if (mix == 3) return launch_kernel(k_score_tc<EPI_LUT, 50, 3>, p, grid, cta_threads(50), st);
-      if (mix == 4) return launch_kernel(k_score_tc<EPI_LUT, 50, 4>, p, grid, cta_threads(50), st);
-      if (mix == 5) return launch_kernel(k_score_tc<EPI_LUT, 50, 5>, p, grid, cta_threads(50), st);
-      if (mix == 6) return launch_kernel(k_score_tc<EPI_LUT, 50, 6>, p, grid, cta_threads(50), st);
+    case 50:
+      // mix: of every kMixPeriod groups of four sites the last one goes through ex2.approx (NEMB200_SCORE_TC_LUT_MIX)
+      if (mix) return launch_kernel(k_score_tc<EPI_LUT, 50, kMixPeriod>, p, grid, cta_threads(50), st);
       return launch_kernel(k_score_tc<EPI_LUT, 50, 50>, p, grid, cta_threads(50), st);
-    }
 #ifndef NEMB200_DEV_S50
     case 8: case -8: return launch_kernel(k_score_tc<EPI_LUT, 8, 8>, p, grid, cta_threads(8), st);
     case 16: case -16: return launch_kernel(k_score_tc<EPI_LUT, 16, 16>, p, grid, cta_threads(16), st);
@@ -1532,6 +1558,7 @@ WsLay ws_layout(const nemb200_dataset *h, int n, bool with_pair) {
 }  // namespace
 
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair) { return ws_layout(h, n, with_pair).total; }
+bool score_tc_has_mix(const nemb200_dataset *h) { return h->lut_valid && h->CS == 50 && h->S == 50; }
 
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
                     int impl, cudaStream_t st, int leave_sms_free, int close) {
@@ -1544,7 +1571,8 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUTM || h->lutm_levels > 0,
                "multi-level table epilogue not available for this dataset (needs 16 <= S <= %d and a range of at most three levels, S=%d)", NEMB200_LUTM_MAX_S, h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_PAIR || h->pair_ok, "pair-merged table epilogue not available for this dataset (S=%d)", h->S);
-  NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUT || h->lut_valid, "exp-table epilogue not valid for this dataset (S=%d)", h->S);
+  NEMB_REQUIRE((impl != NEMB200_SCORE_TC_LUT && impl != NEMB200_SCORE_TC_LUT_MIX) || h->lut_valid, "exp-table epilogue not valid for this dataset (S=%d)", h->S);
+  NEMB_REQUIRE(impl != NEMB200_SCORE_TC_LUT_MIX || score_tc_has_mix(h), "table + ex2 mix needs the column stride 50 (S=%d)", h->S);
   NEMB_REQUIRE(impl != NEMB200_SCORE_TC_EX2 || h->fixed_valid, "fixed-scale ex2 epilogue not valid for this dataset");
   NEMB_REQUIRE(ws_bytes >= score_tc_workspace_bytes(h, n, impl == NEMB200_SCORE_TC_PAIR),
                impl == NEMB200_SCORE_TC_PAIR ? "score workspace too small for the pair-merged kernel: size it with nemb200_score_workspace_bytes_impl"
@@ -1554,7 +1582,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   // propose / accept / finalize kernels (and the first CTAs of its score kernel) never queue behind a full wave
   const int nsm = num_sms() - leave_sms_free > 8 ? num_sms() - leave_sms_free : num_sms();
   const bool pair = impl == NEMB200_SCORE_TC_PAIR;
-  const bool lut = impl == NEMB200_SCORE_TC_LUT;
+  const bool lut = impl == NEMB200_SCORE_TC_LUT || impl == NEMB200_SCORE_TC_LUT_MIX;
   const bool lutm = impl == NEMB200_SCORE_TC_LUTM;
   const int G = pair ? kPairG : (lut ? h->G_lut : (lutm ? h->G_lutm : h->G));  // graphs per MMA N tile of the kernel that will run
   const int CS = pair ? kPairCS : (lutm ? h->CS_lutm : h->CS);
@@ -1625,7 +1653,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
     rc = launch_lut(h, f, nsm, st);
     fbslot = fslot;
   } else if (lut) {
-    rc = launch_lut(h, p, grid, st);
+    rc = launch_lut(h, p, grid, st, impl == NEMB200_SCORE_TC_LUT_MIX);
   } else if (lutm) {
     rc = h->lutm_levels == 2 ? launch_kernel(k_score_tc<EPI_LUTM, 0, 2>, p, grid, cta_threads(0), st, Lay<false, true>::BYTES)
                              : launch_kernel(k_score_tc<EPI_LUTM, 0, 3>, p, grid, cta_threads(0), st, Lay<false, true>::BYTES);

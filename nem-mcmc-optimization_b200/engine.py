@@ -16,7 +16,7 @@ import torch
 from . import _lib
 
 RULE_FULL, RULE_MASKED, RULE_FIT = 0, 1, 2  # FIT: nemb200_mcmc_run only (the reference's per-order edge-weight fit)
-SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5, "pair": 6, "lutm": 7}
+SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5, "pair": 6, "lutm": 7, "lut_mix": 8}
 
 
 def _require_cuda(device=None) -> torch.device:

@@ -181,6 +181,15 @@ def test_score_ragged_E(nb, E):
     assert np.allclose(ds.score_graphs(graphs[:1]), ref[:1], rtol=REL_TC)
 
 
+def test_score_mix_only_at_stride_50(nb):
+    """NEMB200_SCORE_TC_LUT_MIX is refused, loudly, for any column stride but 50."""
+    _, _, D = orc.synth_dataset(30, 500, seed=1)
+    ds = nb.Dataset(D, *orc.nem_constants(0.05, 0.1))
+    bits = ds.order_graphs(np.stack([np.random.default_rng(0).permutation(30) for _ in range(4)]).astype(np.int32))
+    with pytest.raises(RuntimeError, match="mix needs the column stride 50"):
+        ds.score_bits(bits, impl="lut_mix")
+
+
 def test_score_other_error_rates_and_unsupported(nb):
     S, E = 40, 300
     rng = np.random.default_rng(9)
@@ -281,9 +290,13 @@ def test_score_full_size_c3_lut_vs_witness(nb):
     orders = np.stack([rng.permutation(S) for _ in range(n)]).astype(np.int32)
     bits = ds.order_graphs(orders)
     w = ds.score_bits(bits, impl="witness").cpu().numpy()
-    for impl in TC_IMPLS + ["pair"]:
+    for impl in TC_IMPLS + ["pair", "lut_mix"]:
         got = ds.score_bits(bits, impl=impl).cpu().numpy()
         assert np.allclose(got, w, rtol=REL_TC), impl
+    # the sweep entry's AUTO is the table + ex2 mix at this shape; the MCMC loop's AUTO stays with the table-only kernel
+    assert np.array_equal(ds.score_bits(bits).cpu().numpy(), ds.score_bits(bits, impl="lut_mix").cpu().numpy())
+    st = ds.run_chains(orders[:128], 3, 0.01, seed=5, impl="auto")
+    assert np.array_equal(st.curr_scores.cpu().numpy(), ds.score_bits(st.curr_bits, impl="lut").cpu().numpy())
     perm = torch.from_numpy(rng.permutation(n)).to(bits.device)
     got_p = ds.score_bits(bits[perm].contiguous()).cpu().numpy()
     assert np.array_equal(got_p, ds.score_bits(bits).cpu().numpy()[perm.cpu().numpy()])  # deterministic
