@@ -457,9 +457,13 @@ def run_gpu(args, rank, world, local_rank):
     sp = C.c_void_p(stream.cuda_stream)
     ws, _ = ds._score_workspace(CHAINS, "pair" if 33 <= S <= 52 else "auto")  # big enough for the opt-in pair leg too
 
+    pair_auto = bool(ds.pair_ok) and 44 <= S <= 50   # what AUTO of the sweep entry points resolves to (csrc/mcmc.cu: sweep_auto)
+
     def sweep(bits):
-        # closure + score of one batch of candidate graphs in ONE launch: the score kernel's expander warps close every
-        # graph (warp Warshall) before they build the MMA operand (nemb200_closure_score_batch)
+        # closure + score of one batch of candidate graphs through nemb200_closure_score_batch, impl AUTO.  At S = 50 that
+        # is the pair-merged path: k_pair_plan (closes every graph by warp Warshall, pairs its sites, builds the pair
+        # tables) -> pair-merged k_score_tc -> list-mode one-site k_score_tc for graphs the planner gave up on (none here);
+        # finalize fused into the last CTA of each score launch.  Other shapes: ONE launch, closure in the expander warps.
         nb._lib.check(L.nemb200_closure_score_batch(ds._h, C.c_void_p(bits.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
                                                     C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
 
@@ -503,16 +507,19 @@ def run_gpu(args, rank, world, local_rank):
                                             C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
     blocks_kernel = sorted(timed(score_only, K) / K for r in range(REPEATS))
     ms_kernel = blocks_kernel[REPEATS // 2]
-    # the opt-in pair-merged table kernel (two attachment sites per look-up): planner + score, same batch
-    ms_pair = None
-    if ds.S >= 33 and ds.S <= 52 and ds.lut_valid and "pair" not in os.environ.get("BENCH_SKIP", ""):
-        def score_pair(k):
+    # the other score implementations on the same closed batch, for comparison (not part of `value`)
+    other_impls = {}
+    for name in ("lut", "lut_mix", "pair"):
+        if (name == "pair" and not ds.pair_ok) or (name == "lut_mix" and S != 50) or not ds.lut_valid or "impls" in os.environ.get("BENCH_SKIP", ""):
+            continue
+        def score_impl(k, code=nb.engine.SCORE_IMPLS[name]):
             nb._lib.check(L.nemb200_score_batch(ds._h, C.c_void_p(closed.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
-                                                C.c_void_p(ws.data_ptr()), ws.numel(), nb.engine.SCORE_IMPLS["pair"], sp))
+                                                C.c_void_p(ws.data_ptr()), ws.numel(), code, sp))
         with torch.cuda.stream(stream):
             for k in range(3):
-                score_pair(k)
-        ms_pair = timed(score_pair, K) / K
+                score_impl(k)
+        ms_i = timed(score_impl, K) / K
+        other_impls[name] = {"ms_per_batch": ms_i, "graph_scores_per_s": CHAINS / (ms_i * 1e-3)}
 
     # ---- e2e: public host API semantics - pinned host bit rows -> device, closure + score, scores -> host, every
     #      step; Dataset.score_stream double-buffers so the copy of step k+1 overlaps the kernels of step k
@@ -600,21 +607,25 @@ def run_gpu(args, rank, world, local_rank):
                        "rule": "median of the repeats; each block = exactly K steps between barrier + synchronize"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "peak_sustained": tf_sustained, "frac_sustained": achieved / tf_sustained,
-                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_score_tc (tcgen05 kind::i8 + fused logsumexp)",
-                         "score_impl": ds.auto_impl_name() if hasattr(ds, "auto_impl_name") else ("lut" if ds.lut_valid else "ex2"),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": ("k_score_tc<pair> (tcgen05 kind::i8 + fused pair-table logsumexp); kernel_ms is the whole chain of the score call "
+                                    "on closed graphs - k_pair_plan + k_score_tc<pair> + the (empty) list-mode launch: events cannot split a chain, "
+                                    "profiles/r02_launches.md has the per-kernel times") if pair_auto else "k_score_tc (tcgen05 kind::i8 + fused logsumexp)",
+                         "score_impl": "pair" if pair_auto else ("lut" if ds.lut_valid else "ex2"),
                          "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": flops,
                          "exps_per_launch": float((S + 1) * E * CHAINS), "peak_source": how,
-                         # what actually limits the kernel: one shared-memory look-up per (site, E-gene),
-                         # i.e. S * E_pad / 32 LDS wavefronts per graph, against 1 wavefront/clk/SM (the LSU data pipe;
-                         # tools/micro_pipes.cu reaches 0.88 with 16 warps of pure look-ups)
+                         # what actually limits the kernel: one shared-memory look-up per (accumulator column,
+                         # E-gene) - S columns per graph, 32 in the pair-merged kernel - i.e. cols * E_pad / 32 LDS wavefronts per
+                         # graph, against 1 wavefront/clk/SM (the LSU data pipe, shared with the tensor core's operand reads)
                          "co_limit": {"unit": "LDS wavefronts/clk/SM", "peak": 1.0, "measured_ceiling_16_warps": 0.88,
-                                      "achieved": (S * ((E + 127) // 128 * 128) / 32.0 * CHAINS)
+                                      "achieved": ((32 if pair_auto else S) * ((E + 127) // 128 * 128) / 32.0 * CHAINS)
                                                   / (ms_kernel * 1e-3 * (sampler.summary().get("sm_mhz") or 1965.0) * 1e6 * 148)}},
             "e2e": {"value": CHAINS * world * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch_bytes,
-                    "d2h_bytes_per_step": CHAINS * 8, "api": "Dataset.score_stream: closure + score (one fused launch per batch) on pinned host bit rows, scores copied back, copies double-buffered against the kernels"},
-            # timed region of `value`: per step ONE k_score_tc launch (closure fused into its operand expansion, finalize
-            # fused into the last CTA for batches <= 2048 graphs, else a separate k_finalize launch)
-            "gpu_launches": (1 if CHAINS <= 2048 else 2) * K,
+                    "d2h_bytes_per_step": CHAINS * 8, "api": "Dataset.score_stream: closure + score (nemb200_closure_score_batch per batch) on pinned host bit rows, scores copied back, copies double-buffered against the kernels"},
+            # timed region of `value`, per step: pair path = k_pair_plan + k_score_tc<pair> + list-mode k_score_tc (3 launches);
+            # otherwise ONE k_score_tc launch (closure fused into its operand expansion).  Finalize is fused into the last
+            # CTA of the score launches for batches <= 2048 graphs, else a separate k_finalize launch (pair: + a memset)
+            "gpu_launches": ((3 if pair_auto else 1) + (0 if CHAINS <= 2048 else 1)) * K,
             "mcmc": {"value": state.n * world * mc_iters / (ms_mcmc * 1e-3), "unit": "chain-iterations/s", "iters": mc_iters,
                      "chains": state.n * world, "ms_per_iter": ms_mcmc / mc_iters, "accept_rate": acc_rate,
                      "rule": "masked+closure", "collectives": "edge-count all-reduce + best-graph broadcast, once per run",
@@ -623,9 +634,9 @@ def run_gpu(args, rank, world, local_rank):
         }
         if c4 is not None:
             out["config4"] = c4
-        if ms_pair is not None:
-            out["score_pair_merged"] = {"ms_per_launch_incl_planner": ms_pair, "graph_scores_per_s": CHAINS / (ms_pair * 1e-3),
-                                        "note": "impl='pair' (opt-in): k_pair_plan + pair-merged k_score_tc + fallback + finalize"}
+        if other_impls:
+            out["score_impls"] = dict(other_impls, note="nemb200_score_batch on the closed batch per explicit impl: lut = one-site table kernel "
+                                      "(what nemb200_mcmc_run uses), lut_mix = every 4th site group through ex2.approx, pair = planner + pair-merged kernel")
         if world == 1:
             out["edge_fit"] = edge_fit_leg(nb, synth, not args.no_cpu)
             out["mcmc_small"] = small_mcmc_configs(nb, synth, not args.no_cpu)

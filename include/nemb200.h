@@ -49,13 +49,15 @@ enum {
   NEMB200_SCORE_TC_EX2 = 3,  /* tcgen05 GEMM + ex2 epilogue, fixed scale */
   NEMB200_SCORE_TC_EX2_2PASS = 4, /* tcgen05 GEMM + max-subtracted ex2 epilogue (any range) */
   NEMB200_MCMC_FUSED = 5, /* nemb200_mcmc_run only: persistent one-CTA-per-chain kernel (small S*E) */
-  NEMB200_SCORE_TC_PAIR = 6, /* tcgen05 GEMM + pair-merged table epilogue: two attachment sites per look-up (33 <= S <= 52) */
+  NEMB200_SCORE_TC_PAIR = 6, /* tcgen05 GEMM + pair-merged table epilogue: two attachment sites per look-up (33 <= S <= 52): a planner kernel
+                                pairs the sites of every graph (and closes the graph, for nemb200_closure_score_batch), graphs it
+                                cannot plan go through the one-site kernel in the same call.  Three launches, no host round trip.
+                                AUTO of nemb200_score_batch / nemb200_closure_score_batch picks it for 44 <= S <= 50. */
   NEMB200_SCORE_TC_LUTM = 7, /* tcgen05 GEMM + multi-level exp-table epilogue: dynamic ranges of up to ~630 binary orders, 16 <= S <= 125 */
   NEMB200_SCORE_TC_LUT_MIX = 8 /* NEMB200_SCORE_TC_LUT with every fourth group of four attachment sites through ex2.approx
                                   instead of the table (the look-ups bound the kernel on the shared-memory pipe, the MUFU
                                   pipe is idle): about 5 % faster, relative error of a score <= 5e-7 instead of <= 5e-8.
-                                  Column stride 50 (S = 50) only.  AUTO picks it in nemb200_score_batch and
-                                  nemb200_closure_score_batch; nemb200_mcmc_run's AUTO stays with the table-only kernel. */
+                                  Column stride 50 (S = 50) only; never picked by AUTO. */
 };
 
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */
@@ -75,7 +77,8 @@ int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A, double B,
 int nemb200_dataset_destroy(nemb200_dataset *h);
 /* host-side facts about the dataset: fills info[0..7] =
  * {S, E, W, K_pad, graphs_per_tile, lut_valid, scale_log2, n_mtiles}; with n >= 9 also info[8] = number of levels
- * of the multi-level exp table (NEMB200_SCORE_TC_LUTM; 0 = not usable for this dataset) */
+ * of the multi-level exp table (NEMB200_SCORE_TC_LUTM; 0 = not usable for this dataset); with n >= 10 also info[9] = 1 if
+ * the pair-merged path (NEMB200_SCORE_TC_PAIR) is available for this dataset */
 int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int n);
 
 /* ---- transitive closure: replaces utils.ancestor (utils.py:37-54) as called by
@@ -106,12 +109,17 @@ int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_phi_bits, in
                         double *d_scores, void *d_workspace, size_t workspace_bytes, int impl,
                         void *stream);
 
+/* diagnostics: number of graphs of the last NEMB200_SCORE_TC_PAIR launch on `d_workspace` (a batch of n_graphs) that the
+ * pair planner could not plan and that were scored by the one-site kernel instead; synchronises the device; < 0 on error */
+int nemb200_pair_fallback_count(const nemb200_dataset *h, const void *d_workspace, int n_graphs);
+
 /* ---- closure + score in ONE launch: create_nem's utils.ancestor (nem_order_mcmc.py:216-221, utils.py:37-54) followed by
  *      the score above, for candidate graphs that are not transitively closed yet (what a sweep over proposals or
  *      `Dataset.score_graphs(close=True)` needs).  The score kernel's operand-expansion warps close each graph in
  *      registers (the same warp Warshall as nemb200_closure_u32) before they build the MMA operand, so no closed
  *      copy is written to HBM and no second kernel is launched.  Same workspace and `impl` rules as
- *      nemb200_score_batch; NEMB200_SCORE_WITNESS and NEMB200_SCORE_TC_PAIR are not available here (S >= 8). */
+ *      nemb200_score_batch; NEMB200_SCORE_WITNESS is not available here (S >= 8).  With NEMB200_SCORE_TC_PAIR the closure
+ *      runs in the pair planner (which has every graph in shared memory anyway) instead of the score kernel. */
 int nemb200_closure_score_batch(const nemb200_dataset *h, const uint32_t *d_adj_bits, int n_graphs,
                                 double *d_scores, void *d_workspace, size_t workspace_bytes, int impl,
                                 void *stream);

@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
     L.nemb200_score_workspace_bytes_impl.argtypes = [vp, i32, i32]
     L.nemb200_score_batch.argtypes = [vp, vp, i32, vp, vp, sz, i32, vp]
     L.nemb200_closure_score_batch.argtypes = [vp, vp, i32, vp, vp, sz, i32, vp]
+    L.nemb200_pair_fallback_count.argtypes = [vp, vp, i32]
     L.nemb200_order_to_graph.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp]
     L.nemb200_mcmc_workspace_bytes.restype = sz
     L.nemb200_mcmc_workspace_bytes.argtypes = [vp, i32]
@@ -86,7 +87,7 @@ def lib() -> C.CDLL:
 
 EXPORTS = ["nemb200_version", "nemb200_last_error", "nemb200_dataset_bytes", "nemb200_dataset_create",
            "nemb200_dataset_destroy", "nemb200_dataset_info", "nemb200_closure_u32", "nemb200_transitive_reduction_u32",
-           "nemb200_score_workspace_bytes", "nemb200_score_workspace_bytes_impl", "nemb200_score_batch", "nemb200_closure_score_batch", "nemb200_order_to_graph",
+           "nemb200_score_workspace_bytes", "nemb200_score_workspace_bytes_impl", "nemb200_score_batch", "nemb200_closure_score_batch", "nemb200_pair_fallback_count", "nemb200_order_to_graph",
            "nemb200_mcmc_workspace_bytes", "nemb200_mcmc_workspace_bytes_rule", "nemb200_mcmc_run", "nemb200_replica_exchange", "nemb200_replica_exchange_best",
            "nemb200_edge_counts_reduce", "nemb200_cell_ratios", "nemb200_cell_ll_workspace_bytes",
            "nemb200_cell_ll", "nemb200_synth_knockdown", "nemb200_ancestor_x", "nemb200_fit_edges", "nemb200_selftest_partition"]

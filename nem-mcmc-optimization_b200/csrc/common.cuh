@@ -61,7 +61,8 @@ struct nemb200_dataset {
   double lutm_scale[NEMB200_LUTM_LEVELS];  // scale of each level, highest first
   float *lut;         // [64][64] exp table, entry [q][p] = 2^(alpha2*p + beta2*q - s)
   double *sumN;       // [1] A * sum(D)   (nem.py:62 summed over e)
-  int *counters;      // [64] self-resetting completion counters of the score kernel's fused finalize (zero at rest)
+  int *counters;      // [3][64], zero at rest, slot = score workspace (nemb200_cache::ctr_ws): self-resetting completion counters of the
+                      // score kernel's fused finalize, of the pair path's list-mode launch, and that path's list length
   nemb200_cache *cache;  // mutable launcher state (see above); owned by the handle
 };
 

@@ -43,7 +43,7 @@ Layout make_layout(int S, int E) {
   L.lutm = off; off = align_up(off + (lutm_supported(S) ? (size_t)NEMB200_LUTM_LEVELS * NEMB200_LUTM_STRIDE * 4 : 0), 1024);
   L.tile_first = off; off = align_up(off + (lutm_supported(S) ? (size_t)L.n_mtiles : 0), 1024);
   L.sumN = off; off = align_up(off + 8, 1024);
-  L.counters = off; off = align_up(off + 64 * 4, 1024);
+  L.counters = off; off = align_up(off + 192 * 4, 1024);
   L.total = off;
   return L;
 }
@@ -198,7 +198,7 @@ extern "C" int nemb200_dataset_create(const uint8_t *d_D, int S, int E, double A
   h->G = h->G >= 4 ? (h->G & ~3) : 2;           // epilogue warpgroup), or 2 for S > 64
   h->G_lut = h->G;  // the specialised table kernel may use its own tile width (score_tc.cu: tile_graphs)
   int E_pad = L.n_mtiles * 128;
-  if (cudaMemsetAsync(h->counters, 0, 64 * sizeof(int), st) != cudaSuccess) { delete h->cache; free(h); nemb200_set_error("cudaMemsetAsync failed"); return -2; }
+  if (cudaMemsetAsync(h->counters, 0, 192 * sizeof(int), st) != cudaSuccess) { delete h->cache; free(h); nemb200_set_error("cudaMemsetAsync failed"); return -2; }
   k_pack_dcol<<<(E_pad + 255) / 256, 256, 0, st>>>(d_D, S, E, L.W, E_pad, h->dcol);
   k_build_aimg<<<(E_pad * 8 + 255) / 256, 256, 0, st>>>(h->dcol, S, E, L.W, E_pad, 0, h->a_lut);
   h->pair_ok = h->lut_valid && pair_supported(S);
@@ -257,5 +257,6 @@ extern "C" int nemb200_dataset_info(const nemb200_dataset *h, int64_t *info, int
   info[0] = h->S; info[1] = h->E; info[2] = h->W; info[3] = 128; info[4] = h->lut_valid ? h->G_lut : h->G;
   info[5] = h->lut_valid; info[6] = h->scale; info[7] = h->n_mtiles;
   if (n >= 9) info[8] = h->lutm_levels;
+  if (n >= 10) info[9] = h->pair_ok ? 1 : 0;
   return 0;
 }

@@ -285,6 +285,15 @@ extern "C" size_t nemb200_mcmc_workspace_bytes(const nemb200_dataset *h, int n_c
   return one > two ? one : two;
 }
 
+// AUTO of the two sweep entry points (nemb200_score_batch, nemb200_closure_score_batch): the pair-merged path where it is
+// the fastest (measured at E = 10 000, 1024 graphs: S = 40 one-site 78 us / pair 83, S = 44 87 / 83, 47 87 / 83, 50 92 / 85),
+// else the dataset's best one-site kernel.  nemb200_mcmc_run's AUTO does not come through here.
+static bool sweep_auto_is_pair(const nemb200_dataset *h) { return h->pair_ok && h->S >= 44 && h->S <= 50; }
+static int sweep_auto(const nemb200_dataset *h, int impl) {
+  if (impl != NEMB200_SCORE_AUTO || h->S < 8) return impl;
+  return sweep_auto_is_pair(h) ? NEMB200_SCORE_TC_PAIR : impl;
+}
+
 static int score_dispatch(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
                           int impl, cudaStream_t st, int leave_sms_free = 0) {
   if (impl == NEMB200_SCORE_WITNESS || (impl == NEMB200_SCORE_AUTO && h->S < 8)) {
@@ -296,7 +305,8 @@ static int score_dispatch(const nemb200_dataset *h, const uint32_t *phi, int n, 
 
 extern "C" size_t nemb200_score_workspace_bytes_impl(const nemb200_dataset *h, int n_graphs, int impl) {
   if (!h || n_graphs < 0) return 0;
-  size_t a = score_tc_workspace_bytes(h, n_graphs, impl == NEMB200_SCORE_TC_PAIR), b = score_witness_workspace_bytes(n_graphs);
+  size_t a = score_tc_workspace_bytes(h, n_graphs, impl == NEMB200_SCORE_TC_PAIR || (impl == NEMB200_SCORE_AUTO && sweep_auto_is_pair(h))),
+         b = score_witness_workspace_bytes(n_graphs);
   return a > b ? a : b;
 }
 extern "C" size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs) {
@@ -307,7 +317,7 @@ extern "C" int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_p
                                    void *d_workspace, size_t workspace_bytes, int impl, void *stream) {
   NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
   NEMB_REQUIRE(n_graphs == 0 || (d_phi_bits && d_scores && d_workspace), "null device pointer");
-  if (impl == NEMB200_SCORE_AUTO && h->S >= 8 && score_tc_has_mix(h)) impl = NEMB200_SCORE_TC_LUT_MIX;  // sweeps only (see nemb200.h)
+  impl = sweep_auto(h, impl);
   return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream);
 }
 
@@ -315,9 +325,8 @@ extern "C" int nemb200_closure_score_batch(const nemb200_dataset *h, const uint3
                                            void *d_workspace, size_t workspace_bytes, int impl, void *stream) {
   NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
   NEMB_REQUIRE(n_graphs == 0 || (d_adj_bits && d_scores && d_workspace), "null device pointer");
-  NEMB_REQUIRE(impl != NEMB200_SCORE_WITNESS && impl != NEMB200_SCORE_TC_PAIR && h->S >= 8,
-               "closure + score in one launch needs a tensor-core score kernel other than the pair-merged one (S >= 8)");
-  if (impl == NEMB200_SCORE_AUTO && score_tc_has_mix(h)) impl = NEMB200_SCORE_TC_LUT_MIX;
+  NEMB_REQUIRE(impl != NEMB200_SCORE_WITNESS && h->S >= 8, "closure fused into the score needs a tensor-core score kernel (S >= 8)");
+  impl = sweep_auto(h, impl);
   return launch_score_tc(h, d_adj_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, 1);
 }
 

@@ -31,6 +31,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include <vector>
 
 namespace {
 
@@ -93,7 +94,8 @@ struct Params {
   const float *tables;   // pair kernel: per graph kPairCap floats (the graph's pair tables, built by the planner)
   // list mode (fallback pass of the pair kernel): graph ids and their count live in device memory
   const int *glist;
-  const int *n_dev;
+  int *n_dev;          // list mode: number of graphs in glist (reset to 0 by the fused finalize: the planner counts from 0)
+  const int *fbslot;   // pair kernel with fused finalize: graphs with fbslot[g] >= 0 belong to the list-mode launch that follows
   // fused finalize: the last CTA to finish sums the partials of every graph (self-resetting counter); NULL = separate k_finalize
   int *done_counter;
   const double *sumN;
@@ -1247,8 +1249,10 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       __threadfence();
       const unsigned T = (unsigned)n_ntiles * (unsigned)p.n_mtiles;
       const double sumN = *p.sumN;
+      const int ctas_eff = effective_ctas(T, p.n_mtiles, (int)gridDim.x);  // (list mode launches a full grid for a list it cannot see)
       for (int g = threadIdx.x; g < n_graphs; g += cta_threads(S_T)) {
-        const int cnt = slots_of_ntile(g / G, p.n_mtiles, T, (int)gridDim.x);
+        if (p.fbslot != nullptr && __ldcg(p.fbslot + g) >= 0) continue;  // scored by the one-site kernel (list mode)
+        const int cnt = slots_of_ntile(g / G, p.n_mtiles, T, ctas_eff);
         const double *src = p.partials + (size_t)g * p.n_slots;
         // (the first four slots - all there are unless E is huge - are fetched together: one L2 round trip, same order of additions)
         const double s0 = __ldcg(src), s1 = cnt > 1 ? __ldcg(src + 1) : 0.0, s2 = cnt > 2 ? __ldcg(src + 2) : 0.0,
@@ -1258,9 +1262,12 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
         if (cnt > 2) v += s2;
         if (cnt > 3) v += s3;
         for (int c = 4; c < cnt && c < p.n_slots; ++c) v += __ldcg(src + c);
-        p.scores[g] = __fma_rn(NEMB200_LN2, v, sumN);  // (explicit: both finalize paths must round alike)
+        p.scores[p.glist != nullptr ? p.glist[g] : g] = __fma_rn(NEMB200_LN2, v, sumN);  // (explicit: both finalize paths must round alike)
       }
-      if (threadIdx.x == 0) *p.done_counter = 0;  // ready for the next launch on this workspace
+      if (threadIdx.x == 0) {
+        *p.done_counter = 0;  // ready for the next launch on this workspace
+        if (p.n_dev != nullptr) *p.n_dev = 0;  // every CTA has read the list length; the next planner run appends from 0
+      }
 #ifdef NEMB200_PHASES
       if (threadIdx.x == 0 && p.trace != nullptr) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[8007] = (long long)t_; p.trace[8008] = blockIdx.x; }
 #endif
@@ -1280,30 +1287,57 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
 // warp per graph) pairs sites greedily in order of ancestor count, keeps the S - 32 cheapest pairs (tables of
 // at most kPairLim entries, kPairCap per graph) and leaves the other sites single: a 50-site graph becomes 32
 // accumulator columns.  Graphs that cannot be planned are appended to a list and scored by the one-site kernel.
-constexpr int kPlanWindow = 8;     // partner window in sorted order (<= 32)
-constexpr int kPlanThreads = 256;  // one CTA per graph; the planner is latency-bound, so phases are spread over many threads
-__global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__restrict__ phi, int n, int S, int W,
-                                                           const float *__restrict__ tabs, uint8_t *__restrict__ plan,
-                                                           float *__restrict__ tables, int *__restrict__ fbslot,
-                                                           int *__restrict__ flist, int *__restrict__ fcount,
-                                                           long long *__restrict__ trace) {
+constexpr int kPlanWindow = 8;     // partner window in sorted order
+constexpr int kPlanThreads = 128;  // one CTA per graph, all graphs of a 1024-graph batch resident at once (7 CTAs per SM)
+__global__ void __launch_bounds__(kPlanThreads, 7) k_pair_plan(const uint32_t *__restrict__ phi, int n, int S, int W,
+                                                              const float *__restrict__ tabs, uint8_t *__restrict__ plan,
+                                                              float *__restrict__ tables, int *__restrict__ fbslot,
+                                                              int *__restrict__ flist, int *__restrict__ fcount,
+                                                              long long *__restrict__ trace, uint32_t *__restrict__ closed) {
 #define PTRACE(k) do { if (trace != nullptr && blockIdx.x == 500 && threadIdx.x == 0) trace[k] = clock64(); } while (0)
   __shared__ uint32_t s_rows[64 * 2];
-  __shared__ uint4 s_site[64];    // by site j:            {mask word 0, mask word 1, ancestor count, j}
-  __shared__ uint4 s_sorted[64];  // by sorted position r: the same record of the r-th smallest site
-  __shared__ uint4 s_col[kPairCS];  // by accumulator column: {kind, n1 | n2 << 8 | nC << 16, table offset, -}
+  __shared__ uint4 s_site[64];      // by site j:            {mask word 0, mask word 1, ancestor count, j}
+  __shared__ uint4 s_sorted[64];    // by sorted position r: the same record of the r-th smallest site
+  __shared__ uint4 s_col[kPairCS];  // by accumulator column: {kind | ceil(2^16 / w2) << 2, n1 | n2 << 8 | nC << 16, table offset, ceil(2^16 / w1)}
+  __shared__ uint4 s_mask[kPairCS][2];  // by accumulator column: {weight-1 mask (2 words), weight-w1 mask}, {weight-w2 mask, w1, w2}
   __shared__ uint8_t s_plan[2 * kPairCS];
-  __shared__ uint16_t s_cost[64][32];  // pair cost of sorted positions (a, a+1+w), 0xFFFF = not allowed
-  __shared__ float s_tab[57 * 58 / 2];  // V(n, p) = lut[n-p][p] at n(n+1)/2 + p, n <= S <= 56
-  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ __align__(16) uint32_t s_key[64];  // by site: ancestor count << 6 | site
+  __shared__ uint32_t s_cost[32][kPlanWindow];  // pair cost of sorted positions (a, a+1+w), 0xFFFF = not allowed: rows 2k | 2k+1 << 16
+  __shared__ __align__(16) float s_tab[1440];   // V(n, p) = lut[n-p][p] at n(n+1)/2 + p, n <= S <= 52
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  // (rotating the single-warp roles with the CTA's residency slot was measured slower: the hardware already spreads them)
+  const int warp = tid >> 5;
   PTRACE(0);
-  for (int i = tid; i < S * W; i += kPlanThreads) s_rows[i] = phi[(size_t)g * S * W + i];
-  for (int i = tid; i < (S + 1) * (S + 2) / 2; i += kPlanThreads) s_tab[i] = tabs[i];
+  // (the table of V is only needed by the last phase: asynchronous copy, waited for there)
+  for (int i = tid; i * 4 < (S + 1) * (S + 2) / 2; i += kPlanThreads)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + 4 * i)), "l"(tabs + 4 * i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid < S * W) s_rows[tid] = phi[(size_t)g * S * W + tid];  // 33 <= S <= 52, W = 2
   __syncthreads();
+  if (closed != nullptr) {
+    // the batch is not transitively closed yet (nemb200_closure_score_batch): close it here (utils.ancestor, utils.py:37-54,
+    // the same warp Warshall as nemb200_closure_u32) and leave the closed rows for the one-site kernel, should the
+    // graph end up on its list
+    if (warp == 0) {
+      uint32_t r[2][2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) r[t][w] = (t * 32 + lane < S) ? s_rows[(t * 32 + lane) * 2 + w] : 0u;
+      warp_closure<2>(r, S);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (t * 32 + lane < S) {
+          *reinterpret_cast<uint2 *>(s_rows + (t * 32 + lane) * 2) = make_uint2(r[t][0], r[t][1]);
+          *reinterpret_cast<uint2 *>(closed + ((size_t)g * S + t * 32 + lane) * 2) = make_uint2(r[t][0], r[t][1]);
+        }
+    }
+    __syncthreads();
+  }
   PTRACE(1);
   // ancestor-or-self masks (columns of I | Phi) by 32 x 32 bit-block transposes (five shuffle-xor butterfly steps each,
   // like the score kernel's operand expansion): warp w < 2 transposes the two row blocks of column block w, lane l then
-  // holds the mask of site 32 w + l.  (33 <= S <= 52: two words per row.)
+  // holds the mask of site 32 w + l
   if (warp < 2) {
     uint32_t x[2];
 #pragma unroll
@@ -1321,65 +1355,80 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
     x[warp] |= 1u << lane;  // the site itself
     s_site[j] = make_uint4(j < S ? x[0] : 0u, j < S ? x[1] : 0u, j < S ? (uint32_t)(__popc(x[0]) + __popc(x[1])) : (1u << 20), (uint32_t)j);
     s_sorted[j] = make_uint4(0u, 0u, 1u << 20, 255u);
+    s_key[j] = j < S ? ((uint32_t)(__popc(x[0]) + __popc(x[1])) << 6) | (uint32_t)j : 0xFFFFFFFFu;
   }
   __syncthreads();
   PTRACE(2);
-  // sorted by (ancestor count, index)
-  if (tid < S) {
-    const uint4 me = s_site[tid];
+  // sorted by (ancestor count, index): rank = number of smaller keys, four keys per shared-memory load
+  if (warp * 32 + lane < S) {
+    const int j = warp * 32 + lane;
+    const uint32_t key = s_key[j];
     int r = 0;
-#pragma unroll 4
-    for (int k = 0; k < S; ++k) { const uint32_t nk = s_site[k].z; r += (nk < me.z || (nk == me.z && k < tid)) ? 1 : 0; }
-    s_sorted[r] = me;
+    for (int k = 0; k < S; k += 4) {  // (keys of positions >= S are larger than any site's)
+      const uint4 q = *reinterpret_cast<const uint4 *>(s_key + k);
+      r += (q.x < key ? 1 : 0) + (q.y < key ? 1 : 0) + (q.z < key ? 1 : 0) + (q.w < key ? 1 : 0);
+    }
+    s_sorted[r] = s_site[j];
   }
   __syncthreads();
   PTRACE(3);
-  // all pair costs inside the window, in parallel: thread (a, wq) takes partners a+1+wq, a+1+wq+4.  The window is the
+  // all pair costs inside the window, in parallel: thread (a, h) takes partners a+1+4h .. a+4+4h.  The window is the
   // next kPlanWindow sites in sorted order (measured on the benchmark's graph families: 8 finds as many cheap pairs
   // as 32 - no graph falls back - at a quarter of the evaluations)
   {
-    const int a = tid >> 2, wq = tid & 3;
+    const int a = tid >> 1, h = tid & 1;
     const uint4 si = s_sorted[a];
+    uint32_t cost[4];
 #pragma unroll
-    for (int w = wq; w < kPlanWindow; w += 4) {
-      const int idx = a + 1 + w;
-      uint32_t cost = 0xFFFFu;
+    for (int w = 0; w < 4; ++w) {
+      const int idx = a + 1 + 4 * h + w;
+      cost[w] = 0xFFFFu;
       if (a < S && idx < S) {
         const uint4 sj = s_sorted[idx];
         const int nC = __popc(si.x & sj.x) + __popc(si.y & sj.y);
         const uint32_t c = (uint32_t)((nC + 1) * ((int)si.z - nC + 1) * ((int)sj.z - nC + 1));
-        if (c <= (uint32_t)kPairLim) cost = c;
+        if (c <= (uint32_t)kPairLim) cost[w] = c;
       }
-      s_cost[a][w] = (uint16_t)cost;
     }
+    uint16_t *dst = reinterpret_cast<uint16_t *>(&s_cost[a >> 1][4 * h]) + (a & 1);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) dst[2 * w] = (uint16_t)cost[w];
   }
   __syncthreads();
   PTRACE(4);
   const int need = S - kPairCS;
   if (warp == 0) {
-    // greedy matching over sorted positions: the first free position takes the cheapest free partner among the next 32
-    uint32_t u0 = 0, u1 = S >= 64 ? 0u : ~((S > 32 ? (1u << (S - 32)) : 1u) - 1u);  // positions >= S are "used"
-    if (S <= 32) { u0 = S == 32 ? 0u : ~((1u << S) - 1u); u1 = 0xffffffffu; }
+    // greedy matching over sorted positions: every position that is still free takes the cheapest free partner of its
+    // window.  Straight-line code over the positions (compile-time shifts, the window costs of lane w preloaded in
+    // registers): the chain per pairing round is a funnel shift, one warp reduction and the mask update.
+    uint32_t u0 = 0, u1 = ~((1u << (S - 32)) - 1u);  // positions >= S are "used" (33 <= S <= 52)
     int npairs = 0;
     uint32_t my_cost = 0xFFFFFFFFu, my_a = 0, my_b = 0;  // lane k keeps pair k
-    while (true) {
-      const int a = ~u0 ? __ffs(~u0) - 1 : (~u1 ? 32 + __ffs(~u1) - 1 : 64);
-      if (a >= S - 1) break;
-      if (a < 32) u0 |= 1u << a; else u1 |= 1u << (a - 32);  // paired below or left single
-      const int idx = a + 1 + lane;
-      const uint32_t c = lane < kPlanWindow ? s_cost[a][lane] : 0xFFFFu;
-      const bool taken = idx >= 64 || ((((idx < 32 ? u0 : u1) >> (idx & 31)) & 1u) != 0u);
-      const uint32_t packed = (c == 0xFFFFu || taken) ? 0xFFFFFFFFu : ((c << 8) | (uint32_t)lane);
-      const uint32_t best = __reduce_min_sync(0xffffffffu, packed);
-      if (best == 0xFFFFFFFFu) continue;
-      const int b = a + 1 + (int)(best & 255u);
-      if (b < 32) u0 |= 1u << b; else u1 |= 1u << (b - 32);
-      if (lane == npairs) { my_cost = best >> 8; my_a = (uint32_t)a; my_b = (uint32_t)b; }
-      ++npairs;  // at most S/2 <= 32
+    const int wl = lane & (kPlanWindow - 1);
+    uint32_t cst[26];
+#pragma unroll
+    for (int k = 0; k < 26; ++k) cst[k] = s_cost[k][wl];
+#pragma unroll
+    for (int a = 0; a < 51; ++a) {
+      const bool used = a < 32 ? ((u0 >> a) & 1u) != 0u : ((u1 >> (a - 32)) & 1u) != 0u;
+      if (a < S - 1 && !used) {  // warp-uniform
+        // bit l of `win`: position a + 1 + l is taken
+        const uint32_t win = a + 1 < 32 ? __funnelshift_r(u0, u1, a + 1) : (u1 >> (a + 1 - 32));
+        const uint32_t c = (a & 1) ? (cst[a >> 1] >> 16) : (cst[a >> 1] & 0xFFFFu);
+        const uint32_t packed = (lane >= kPlanWindow || c == 0xFFFFu || ((win >> lane) & 1u)) ? 0xFFFFFFFFu : ((c << 8) | (uint32_t)lane);
+        const uint32_t best = __reduce_min_sync(0xffffffffu, packed);
+        if (best != 0xFFFFFFFFu) {
+          const int b = a + 1 + (int)(best & 255u);
+          if (b < 32) u0 |= 1u << b; else u1 |= 1u << (b - 32);
+          if (lane == npairs) { my_cost = best >> 8; my_a = (uint32_t)a; my_b = (uint32_t)b; }
+          ++npairs;  // at most S/2 <= 32
+        }
+      }
     }
     PTRACE(5);
     // keep the `need` cheapest pairs
     int rank = 0;
+#pragma unroll 8
     for (int m = 0; m < 32; ++m) {
       const uint32_t cm = __shfl_sync(0xffffffffu, my_cost, m);
       rank += (cm < my_cost || (cm == my_cost && m < lane)) ? 1 : 0;
@@ -1403,7 +1452,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
       sel0 = __reduce_or_sync(0xffffffffu, sel0);
       sel1 = __reduce_or_sync(0xffffffffu, sel1);
       // single sites fill the remaining columns (need + (S - 2*need) == kPairCS exactly)
-      const uint32_t full0 = S >= 32 ? 0xffffffffu : ((1u << S) - 1u), full1 = S > 32 ? ((1u << (S - 32)) - 1u) : 0u;
+      const uint32_t full0 = 0xffffffffu, full1 = (1u << (S - 32)) - 1u;
       const uint32_t free0 = ~sel0 & full0, free1 = ~sel1 & full1;
       const uint32_t below = (1u << lane) - 1u;
       if ((free0 >> lane) & 1u) { const int c = need + __popc(free0 & below); s_plan[c * 2] = (uint8_t)lane; s_plan[c * 2 + 1] = 255; }
@@ -1411,14 +1460,14 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
     }
     __syncwarp();
     PTRACE(6);
-    // lane c builds column c: 64 B-operand bytes (constant rows left 0 for the expander) + meta
+    // lane c: shape of column c - the masks of weight 1 / w1 / w2, the table's size and offset
     const int j1 = s_plan[lane * 2], j2 = s_plan[lane * 2 + 1];
-    uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    uint32_t a0 = 0, a1m = 0, b0 = 0, b1 = 0;
     int kind = 0;
-    if (j1 < S) { kind = 1; a0 = s_site[j1].x; a1 = s_site[j1].y; }
+    if (j1 < S) { kind = 1; a0 = s_site[j1].x; a1m = s_site[j1].y; }
     if (kind == 1 && j2 < S) { kind = 2; b0 = s_site[j2].x; b1 = s_site[j2].y; }
-    const uint32_t c0 = a0 & b0, c1 = a1 & b1;
-    const int n1 = __popc(a0) + __popc(a1), n2 = __popc(b0) + __popc(b1), nC = __popc(c0) + __popc(c1);
+    const uint32_t c0 = a0 & b0, c1w = a1m & b1;
+    const int n1 = __popc(a0) + __popc(a1m), n2 = __popc(b0) + __popc(b1), nC = __popc(c0) + __popc(c1w);
     const int d1 = n1 - nC, d2 = n2 - nC;
     const uint32_t w1 = (uint32_t)(nC + 1), w2 = w1 * (uint32_t)(d1 + 1);
     const uint32_t tsz = kind == 2 ? w2 * (uint32_t)(d2 + 1) : 0u;
@@ -1429,45 +1478,51 @@ __global__ void __launch_bounds__(kPlanThreads) k_pair_plan(const uint32_t *__re
       if (lane >= o) incl += t2;
     }
     const uint32_t toff = incl - tsz;
-    // weight 1 on the common ancestors (single site: all of them), w1 / w2 on the two differences
-    const uint32_t one0 = kind == 2 ? c0 : a0, one1 = kind == 2 ? c1 : a1;
-    const uint32_t x0 = kind == 2 ? (a0 & ~c0) : 0u, x1 = kind == 2 ? (a1 & ~c1) : 0u;
-    const uint32_t y0 = kind == 2 ? (b0 & ~c0) : 0u, y1 = kind == 2 ? (b1 & ~c1) : 0u;
-    uint32_t words[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const uint32_t o = ((q < 8 ? one0 : one1) >> ((q & 7) * 4)) & 0xFu, x = ((q < 8 ? x0 : x1) >> ((q & 7) * 4)) & 0xFu,
-                     y = ((q < 8 ? y0 : y1) >> ((q & 7) * 4)) & 0xFu;
-      words[q] = ((o * 0x00204081u) & 0x01010101u) + ((x * 0x00204081u) & 0x01010101u) * w1 + ((y * 0x00204081u) & 0x01010101u) * w2;
-    }
-    uint4 *dst = reinterpret_cast<uint4 *>(plan + ((size_t)g * kPairCS + lane) * kPlanColBytes);
-    dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
-    dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
-    dst[2] = make_uint4(words[8], words[9], words[10], words[11]);
-    dst[3] = make_uint4(words[12], words[13], words[14], words[15]);
-    // meta: kind | n1<<8 | n2<<16 | nC<<24 ; d1 | d2<<8 | toff<<16 ; table entries of the whole graph
     const uint32_t total_g = __shfl_sync(0xffffffffu, incl, 31);
-    dst[4] = make_uint4((uint32_t)kind | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16) | ((uint32_t)nC << 24),
-                        (uint32_t)d1 | ((uint32_t)d2 << 8) | (toff << 16), total_g, 0u);
-    s_col[lane] = make_uint4((uint32_t)kind, (uint32_t)n1 | ((uint32_t)n2 << 8) | ((uint32_t)nC << 16), toff, tsz);
+    // weight 1 on the common ancestors (single site: all of them), w1 / w2 on the two differences
+    s_mask[lane][0] = make_uint4(kind == 2 ? c0 : a0, kind == 2 ? c1w : a1m, kind == 2 ? (a0 & ~c0) : 0u, kind == 2 ? (a1m & ~c1w) : 0u);
+    s_mask[lane][1] = make_uint4(kind == 2 ? (b0 & ~c0) : 0u, kind == 2 ? (b1 & ~c1w) : 0u, w1, w2);
+    s_col[lane] = make_uint4((uint32_t)kind | (((65536u + w2 - 1u) / w2) << 2), (uint32_t)n1 | ((uint32_t)n2 << 8) | ((uint32_t)nC << 16), toff, (65536u + w1 - 1u) / w1);
+    // meta: kind | n1<<8 | n2<<16 | nC<<24 ; d1 | d2<<8 | toff<<16 ; table entries of the whole graph
+    reinterpret_cast<uint4 *>(plan + ((size_t)g * kPairCS + lane) * kPlanColBytes)[4] =
+        make_uint4((uint32_t)kind | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16) | ((uint32_t)nC << 24),
+                   (uint32_t)d1 | ((uint32_t)d2 << 8) | (toff << 16), total_g, 0u);
   }
   __syncthreads();
   PTRACE(7);
+  // thread (c, quarter): 16 of column c's 64 B-operand bytes (constant rows left 0 for the expander)
+  {
+    const int c = tid >> 2, qd = tid & 3;
+    const uint4 m0 = s_mask[c][0], m1 = s_mask[c][1];
+    const uint32_t one = qd < 2 ? m0.x : m0.y, xx = qd < 2 ? m0.z : m0.w, yy = qd < 2 ? m1.x : m1.y, w1 = m1.z, w2 = m1.w;
+    uint32_t words[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sh = ((qd & 1) * 4 + q) * 4;
+      const uint32_t o = (one >> sh) & 0xFu, x = (xx >> sh) & 0xFu, y = (yy >> sh) & 0xFu;
+      words[q] = ((o * 0x00204081u) & 0x01010101u) + ((x * 0x00204081u) & 0x01010101u) * w1 + ((y * 0x00204081u) & 0x01010101u) * w2;
+    }
+    reinterpret_cast<uint4 *>(plan + ((size_t)g * kPairCS + c) * kPlanColBytes)[qd] = make_uint4(words[0], words[1], words[2], words[3]);
+  }
   // the pair tables of this graph, entry pc + w1*p1 + w2*p2 = V(n1, pc+p1) + V(n2, pc+p2), V(n, p) = lut[n-p][p]
-  // (the score kernel copies the block into shared memory with one bulk copy per graph); one warp per column
+  // (the score kernel copies the block into shared memory with one bulk copy per graph).  One warp per pair column
+  // (pairs are the first `need` columns, cheapest first), a lane per entry (mixed-radix digits by two multiply-shifts).
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
   float *tg = tables + (size_t)g * kPairCap;
-  for (int c = warp; c < kPairCS; c += kPlanThreads / 32) {
+  for (int c = warp; c < need; c += kPlanThreads / 32) {
     const uint4 cm = s_col[c];
-    if (cm.x != 2u) continue;  // warp-uniform
+    if ((cm.x & 3u) != 2u) continue;  // warp-uniform
     const int cn1 = (int)(cm.y & 255u), cn2 = (int)((cm.y >> 8) & 255u), cnC = (int)(cm.y >> 16);
-    const int cd1 = cn1 - cnC, cd2 = cn2 - cnC, cw1 = cnC + 1;
+    const int cw1 = cnC + 1, cw2 = cw1 * (cn1 - cnC + 1), tsz = cw2 * (cn2 - cnC + 1);
+    const uint32_t m1 = cm.w, m2 = cm.x >> 2;  // ceil(2^16 / cw1), ceil(2^16 / cw2): x / cw = (x * m) >> 16 for x * cw < 2^16
     float *td = tg + cm.z;
     const float *t1 = s_tab + cn1 * (cn1 + 1) / 2, *t2 = s_tab + cn2 * (cn2 + 1) / 2;
-    for (int p2 = 0; p2 <= cd2; ++p2)
-      for (int p1 = 0; p1 <= cd1; ++p1) {
-        float *row = td + cw1 * (p1 + (cd1 + 1) * p2);
-        for (int pc = lane; pc < cw1; pc += 32) row[pc] = t1[pc + p1] + t2[pc + p2];
-      }
+    for (int i = lane; i < tsz; i += 32) {
+      const int p2 = (int)(((uint32_t)i * m2) >> 16), e = i - p2 * cw2;
+      const int p1 = (int)(((uint32_t)e * m1) >> 16), pc = e - p1 * cw1;
+      td[i] = t1[pc + p1] + t2[pc + p2];
+    }
   }
   PTRACE(8);
 #undef PTRACE
@@ -1538,7 +1593,7 @@ int launch_lut(const nemb200_dataset *h, const Params &p, int grid, cudaStream_t
 }
 
 // workspace carve-up (bytes from the base)
-struct WsLay { size_t fcount, partials, fb_partials, plan, tables, fbslot, flist, trace, total; };
+struct WsLay { size_t fcount, partials, fb_partials, plan, tables, fbslot, flist, closed, trace, total; };
 WsLay ws_layout(const nemb200_dataset *h, int n, bool with_pair) {
   WsLay w;
   const bool pr = with_pair && h->pair_ok;
@@ -1550,6 +1605,7 @@ WsLay ws_layout(const nemb200_dataset *h, int n, bool with_pair) {
   w.tables = off; off = align_up(off + (pr ? (size_t)n * kPairCap * 4 : 0), 256);
   w.fbslot = off; off = align_up(off + (pr ? (size_t)n * 4 : 0), 256);
   w.flist = off; off = align_up(off + (pr ? (size_t)(n + 16) * 4 : 0), 256);
+  w.closed = off; off = align_up(off + (pr ? (size_t)n * h->S * h->W * 4 : 0), 256);  // closed rows (closure fused into the planner)
   w.trace = off; off += 8 * 8192;  // diagnostics time line
   w.total = off;
   return w;
@@ -1607,13 +1663,13 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   p.k1 = (float)(-kappa2 / 252.0);
   p.kc = (float)(256.0 * kappa2 / 252.0 + h->beta2);
   p.scale = impl == NEMB200_SCORE_TC_EX2_2PASS ? 0.f : (float)h->scale;
-  p.plan = nullptr; p.tables = nullptr; p.glist = nullptr; p.n_dev = nullptr;
+  p.plan = nullptr; p.tables = nullptr; p.glist = nullptr; p.n_dev = nullptr; p.fbslot = nullptr;
   p.close = close ? 1 : 0;
-  NEMB_REQUIRE(!(close && pair), "the pair-merged kernel plans on closed graphs: close them first (nemb200_closure_u32)");
   p.done_counter = nullptr; p.sumN = h->sumN; p.scores = scores;
   // (one CTA finalizing a large batch is slower than the separate, fully parallel kernel; in the two-group MCMC loop
   //  the separate kernel overlaps with the other group's score kernel and the tail of a fused one does not)
-  if (!pair && n <= 2048 && leave_sms_free == 0) {
+  int ctr_slot = -1;
+  if (n <= 2048 && leave_sms_free == 0) {
     // one self-resetting completion counter per distinct workspace (launches that share a workspace are ordered by
     // the caller anyway); when the pool is exhausted the separate finalize kernel is used
     // (the counters themselves sit in the dataset workspace, which the library zeroed: caller memory is not zero at rest)
@@ -1625,6 +1681,7 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
       if (slot < 0 && hm->n_ctr < 64) { slot = hm->n_ctr++; hm->ctr_ws[slot] = ws; }
     }
     if (slot >= 0) p.done_counter = h->counters + slot;
+    ctr_slot = slot;
   }
   const int grid = effective_ctas(T, h->n_mtiles, nsm);
   int rc;
@@ -1634,19 +1691,34 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
   const int *fbslot = nullptr;
   if (pair) {
     // plan -> pair-merged kernel -> one-site kernel over the (device-side) list of graphs the planner gave up on
-    int *fcount = reinterpret_cast<int *>(wb + wl.fcount), *flist = reinterpret_cast<int *>(wb + wl.flist);
+    // Fused finalize (a counter slot was found above): the last CTA of the pair kernel writes the scores of the planned
+    // graphs, the last CTA of the list-mode launch those of the listed ones and puts the list length back to zero -
+    // three launches (plan, score, list), no memset and no finalize kernel.  The list length then lives beside the
+    // completion counters in the dataset's workspace (zero at rest; caller memory is not).
+    const bool fused = p.done_counter != nullptr;
+    int *fcount = fused ? h->counters + 128 + ctr_slot : reinterpret_cast<int *>(wb + wl.fcount);
+    int *flist = reinterpret_cast<int *>(wb + wl.flist);
     int *fslot = reinterpret_cast<int *>(wb + wl.fbslot);
     uint8_t *plan = wb + wl.plan;
-    NEMB_CHECK_CUDA(cudaMemsetAsync(fcount, 0, sizeof(int), st));
+    static bool planned_once = false;  // (diagnostics, bit 128: after the first call, time the score kernels alone on the plan it left in the workspace)
+    if (!(p.debug & 128) || !planned_once) {
+      planned_once = true;
+      if (!fused) NEMB_CHECK_CUDA(cudaMemsetAsync(fcount, 0, sizeof(int), st));
+      k_pair_plan<<<n, kPlanThreads, 0, st>>>(phi, n, h->S, h->W, h->tabs, plan, reinterpret_cast<float *>(wb + wl.tables), fslot, flist, fcount,
+                                           (p.debug & 64) ? reinterpret_cast<long long *>(wb + wl.trace) : nullptr,
+                                           close ? reinterpret_cast<uint32_t *>(wb + wl.closed) : nullptr);
+      NEMB_CHECK_CUDA(cudaGetLastError());
+    }
+    p.close = 0;  // (the planner closed the batch; the pair kernel reads the plan, the list-mode launch the closed rows)
     float *tables = reinterpret_cast<float *>(wb + wl.tables);
-    k_pair_plan<<<n, kPlanThreads, 0, st>>>(phi, n, h->S, h->W, h->tabs, plan, tables, fslot, flist, fcount,
-                                         (p.debug & 64) ? reinterpret_cast<long long *>(wb + wl.trace) : nullptr);
-    NEMB_CHECK_CUDA(cudaGetLastError());
     p.plan = plan; p.tables = tables;
+    if (fused) p.fbslot = fslot;
     rc = launch_kernel(k_score_tc<EPI_LUT, kPairCS, kPairCS, true>, p, grid, cta_threads(kPairCS), st, Lay<true>::BYTES);
     if (rc) return rc;
     Params f = p;
-    f.a_img = h->a_lut; f.plan = nullptr; f.glist = flist; f.n_dev = fcount;
+    f.a_img = h->a_lut; f.plan = nullptr; f.glist = flist; f.n_dev = fcount; f.fbslot = nullptr;
+    if (close) f.phi = reinterpret_cast<const uint32_t *>(wb + wl.closed);
+    if (fused) f.done_counter = h->counters + 64 + ctr_slot;
     f.partials = reinterpret_cast<double *>(wb + wl.fb_partials);
     f.G = h->G_lut; f.CS = h->CS; f.nmma = (f.G * f.CS + 15) / 16 * 16; f.ksteps = (h->S + 1 + 31) / 32;
     f.trace = nullptr;
@@ -1673,6 +1745,19 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
                                                reinterpret_cast<const double *>(wb + wl.fb_partials), h->G_lut);
   NEMB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Diagnostics (tests): how many graphs of the last NEMB200_SCORE_TC_PAIR launch on this workspace the planner gave up on
+// (they went through the one-site kernel).  Synchronises the device.
+extern "C" int nemb200_pair_fallback_count(const nemb200_dataset *h, const void *d_workspace, int n_graphs) {
+  NEMB_REQUIRE(h != nullptr && d_workspace != nullptr && n_graphs >= 0 && h->pair_ok, "bad handle / workspace, or no pair-merged kernel for this dataset");
+  const WsLay wl = ws_layout(h, n_graphs, true);
+  std::vector<int> slot((size_t)n_graphs);
+  NEMB_CHECK_CUDA(cudaDeviceSynchronize());
+  NEMB_CHECK_CUDA(cudaMemcpy(slot.data(), reinterpret_cast<const uint8_t *>(d_workspace) + wl.fbslot, sizeof(int) * (size_t)n_graphs, cudaMemcpyDeviceToHost));
+  int c = 0;
+  for (int v : slot) c += v >= 0 ? 1 : 0;
+  return c;
 }
 
 // Host-only self-test of the tile partition (no device work): every flat tile is owned by exactly one CTA, the items a

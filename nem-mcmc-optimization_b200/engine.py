@@ -193,11 +193,12 @@ class Dataset:
                                             nbytes, _stream_ptr(st), C.byref(h)))
         self._h = h
         st.synchronize()  # d (the uint8 copy) may be freed after this
-        info = (C.c_int64 * 9)()
-        _lib.check(L.nemb200_dataset_info(self._h, info, 9))
+        info = (C.c_int64 * 10)()
+        _lib.check(L.nemb200_dataset_info(self._h, info, 10))
         self.W, self.graphs_per_tile, self.lut_valid, self.scale_log2, self.n_mtiles = (
             int(info[2]), int(info[4]), bool(info[5]), int(info[6]), int(info[7]))
         self.lutm_levels = int(info[8])  # levels of the multi-level exp table (16 <= S <= 125), 0 = not usable
+        self.pair_ok = bool(info[9])     # pair-merged score path available (33 <= S <= 52, single-scale table valid)
         self._score_ws = None
 
     def __del__(self):
@@ -224,8 +225,9 @@ class Dataset:
         return max(per_tile * n_tiles // 1024 * 1024, 1024)
 
     def _fusable(self, code) -> bool:
-        """closure + score in one launch (nemb200_closure_score_batch): every tensor-core kernel but the pair-merged one."""
-        return self.S >= 8 and code not in (SCORE_IMPLS["witness"], SCORE_IMPLS["pair"])
+        """closure fused into the score (nemb200_closure_score_batch): every tensor-core kernel (the pair-merged path closes
+        in its planner, the others in the score kernel's operand expansion)."""
+        return self.S >= 8 and code != SCORE_IMPLS["witness"]
 
     def score_bits(self, bits: torch.Tensor, impl="auto", out: torch.Tensor | None = None, stream=None,
                    close: bool = False) -> torch.Tensor:

@@ -269,7 +269,7 @@ def test_score_pair_merged_kernel(nb, S):
     w = ds.score_graphs(graphs, impl="witness")
     got = ds.score_graphs(graphs, impl="pair")
     assert np.allclose(got, w, rtol=REL_TC), np.abs(got / w - 1).max()
-    n_fb = int(ds._score_ws[:4].view(torch.int32).item())   # graphs that took the fallback route
+    n_fb = nb._lib.lib().nemb200_pair_fallback_count(ds._h, ds._score_ws.data_ptr(), len(graphs))   # graphs that took the fallback route
     assert (0 < n_fb or S < 47) and n_fb < len(graphs), n_fb
     assert np.allclose(ds.score_graphs(graphs, impl="lut"), w, rtol=REL_TC)
     ref = c_oracle.score_batch(graphs[:8], D, A, B, nthreads=4)
@@ -293,8 +293,8 @@ def test_score_full_size_c3_lut_vs_witness(nb):
     for impl in TC_IMPLS + ["pair", "lut_mix"]:
         got = ds.score_bits(bits, impl=impl).cpu().numpy()
         assert np.allclose(got, w, rtol=REL_TC), impl
-    # the sweep entry's AUTO is the table + ex2 mix at this shape; the MCMC loop's AUTO stays with the table-only kernel
-    assert np.array_equal(ds.score_bits(bits).cpu().numpy(), ds.score_bits(bits, impl="lut_mix").cpu().numpy())
+    # the sweep entry's AUTO is the pair-merged path at this shape; the MCMC loop's AUTO stays with the one-site table kernel
+    assert np.array_equal(ds.score_bits(bits).cpu().numpy(), ds.score_bits(bits, impl="pair").cpu().numpy())
     st = ds.run_chains(orders[:128], 3, 0.01, seed=5, impl="auto")
     assert np.array_equal(st.curr_scores.cpu().numpy(), ds.score_bits(st.curr_bits, impl="lut").cpu().numpy())
     perm = torch.from_numpy(rng.permutation(n)).to(bits.device)
@@ -362,10 +362,10 @@ def test_order_to_graph_vs_oracle(nb, S):
 
 
 @pytest.mark.parametrize("S,E,n,impl", [(10, 100, 37, "auto"), (20, 300, 64, "auto"), (50, 1000, 130, "lut"), (50, 1000, 9, "ex2_2pass"),
-                                        (33, 257, 21, "auto"), (64, 300, 17, "auto"), (100, 700, 23, "lutm"), (128, 200, 9, "auto")])
+                                        (50, 1000, 130, "pair"), (50, 1000, 130, "auto"), (40, 500, 66, "pair"), (33, 257, 21, "auto"), (64, 300, 17, "auto"), (100, 700, 23, "lutm"), (128, 200, 9, "auto")])
 def test_closure_fused_into_score_kernel(nb, S, E, n, impl):
-    """nemb200_closure_score_batch (closure inside the score kernel's operand expansion, one launch) == closure kernel +
-    score kernel == the oracle's closure + score, on unclosed DAGs and on digraphs with cycles; the input is not modified."""
+    """nemb200_closure_score_batch (closure inside the score kernel's operand expansion, one launch - or, for the pair-merged
+    path, inside its planner) == closure kernel + score kernel == the oracle's closure + score, on unclosed DAGs and on digraphs with cycles; the input is not modified."""
     _, _, D = orc.synth_dataset(S, E, seed=S)
     A, B = orc.nem_constants(0.05, 0.1)
     rng = np.random.default_rng(S + n)
