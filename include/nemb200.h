@@ -57,7 +57,7 @@ enum {
   NEMB200_SCORE_TC_LUT_MIX = 8 /* NEMB200_SCORE_TC_LUT with every fourth group of four attachment sites through ex2.approx
                                   instead of the table (the look-ups bound the kernel on the shared-memory pipe, the MUFU
                                   pipe is idle): about 5 % faster, relative error of a score <= 5e-7 instead of <= 5e-8.
-                                  Column stride 50 (S = 50) only; never picked by AUTO. */
+                                  Column stride 50 (S = 50) only; AUTO of nemb200_mcmc_run's kernel loop at that stride. */
 };
 
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */

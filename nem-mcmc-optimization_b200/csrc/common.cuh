@@ -96,7 +96,7 @@ int launch_score_witness(const nemb200_dataset *h, const uint32_t *phi, int n, d
 size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair = false);
 bool score_tc_has_mix(const nemb200_dataset *h);  // NEMB200_SCORE_TC_LUT_MIX available for this dataset
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                    int impl, cudaStream_t st, int leave_sms_free = 0, int close = 0);
+                    int impl, cudaStream_t st, int leave_sms_free = 0, int close = 0, int pdl = 0);
 
 size_t fit_pipeline_workspace_bytes(const nemb200_dataset *h, int n);
 int launch_fit_pipeline(const nemb200_dataset *h, int n, uint32_t *prop_bits, double *prop_scores, void *ws, double w0,

@@ -294,13 +294,19 @@ static int sweep_auto(const nemb200_dataset *h, int impl) {
   return sweep_auto_is_pair(h) ? NEMB200_SCORE_TC_PAIR : impl;
 }
 
+// a launch outside stream capture may carry the programmatic-dependent-launch attribute (score_tc.cu: launch_ex)
+static int pdl_ok(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone ? 1 : 0;
+}
+
 static int score_dispatch(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                          int impl, cudaStream_t st, int leave_sms_free = 0) {
+                          int impl, cudaStream_t st, int leave_sms_free = 0, int pdl = 0) {
   if (impl == NEMB200_SCORE_WITNESS || (impl == NEMB200_SCORE_AUTO && h->S < 8)) {
     NEMB_REQUIRE(ws_bytes >= score_witness_workspace_bytes(n), "score workspace too small");
     return launch_score_witness(h, phi, n, scores, ws, st);
   }
-  return launch_score_tc(h, phi, n, scores, ws, ws_bytes, impl, st, leave_sms_free);
+  return launch_score_tc(h, phi, n, scores, ws, ws_bytes, impl, st, leave_sms_free, 0, pdl);
 }
 
 extern "C" size_t nemb200_score_workspace_bytes_impl(const nemb200_dataset *h, int n_graphs, int impl) {
@@ -318,7 +324,7 @@ extern "C" int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_p
   NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
   NEMB_REQUIRE(n_graphs == 0 || (d_phi_bits && d_scores && d_workspace), "null device pointer");
   impl = sweep_auto(h, impl);
-  return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream);
+  return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, pdl_ok((cudaStream_t)stream));
 }
 
 extern "C" int nemb200_closure_score_batch(const nemb200_dataset *h, const uint32_t *d_adj_bits, int n_graphs, double *d_scores,
@@ -327,7 +333,7 @@ extern "C" int nemb200_closure_score_batch(const nemb200_dataset *h, const uint3
   NEMB_REQUIRE(n_graphs == 0 || (d_adj_bits && d_scores && d_workspace), "null device pointer");
   NEMB_REQUIRE(impl != NEMB200_SCORE_WITNESS && h->S >= 8, "closure fused into the score needs a tensor-core score kernel (S >= 8)");
   impl = sweep_auto(h, impl);
-  return launch_score_tc(h, d_adj_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, 1);
+  return launch_score_tc(h, d_adj_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, 1, pdl_ok((cudaStream_t)stream));
 }
 
 extern "C" int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_t *d_out_bits, void *stream) {
@@ -378,6 +384,11 @@ extern "C" int nemb200_mcmc_run(const nemb200_dataset *h, int n, int64_t n_iters
     return launch_mcmc_fused(h, n, n_iters, iter0, burn_in, d_gamma, sp, seed, chain_offset, rule_arg, d_cand_bits, use_nem_arg,
                              resume, d_orders, d_curr_scores, d_curr_bits, d_best_scores, d_best_orders, d_best_bits,
                              d_accept, d_edge_counts, d_score_trace, st);
+  // AUTO of the kernel loop at the column stride 50: the one-site table kernel with a quarter of the sites through ex2.approx
+  // (NEMB200_SCORE_TC_LUT_MIX: 94 -> 87 us per iteration of 1024 chains at S=50, E=10k; the pair-merged path does not pay
+  // here, its planner would run per group and iteration: 95 us).  Scores then carry a relative error of <= 5e-7 instead
+  // of <= 5e-8 - still 200 times inside the 1e-4 the accept step is specified to.
+  if (score_impl == NEMB200_SCORE_AUTO && S >= 8 && score_tc_has_mix(h)) score_impl = NEMB200_SCORE_TC_LUT_MIX;
   constexpr int kUnroll = 16;  // iterations per captured CUDA graph
   const int thr = kWarpsPerBlock * 32;
   nemb200_cache *hm = h->cache;  // graph cache + side stream: mutable launcher state, serialised per handle

@@ -775,7 +775,15 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
   constexpr int kStages = L::STAGES;
   static_assert(!PAIR || (EPI == EPI_LUT && S_T == kPairCS), "the pair kernel is the 32-column table kernel");
   extern __shared__ __align__(1024) uint8_t smem[];
-  if (p.n_dev != nullptr && *p.n_dev == 0) return;  // list mode with an empty list: nothing to do (uniform exit)
+  // Programmatic dependent launch (the sweep entry points launch with cudaLaunchAttributeProgrammaticStreamSerialization):
+  // the next kernel of the stream may be set up while this grid runs, and this grid runs its prologue - barriers, TMEM,
+  // the exp table (dataset constants) - while its predecessor drains; griddepcontrol.wait (a no-op for a plain launch)
+  // stands before the first access to anything the predecessor may produce or still read: graphs, plan, workspace.
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (p.n_dev != nullptr) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (*p.n_dev == 0) return;  // list mode with an empty list: nothing to do (uniform exit)
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) PHASE(0);
   const uint32_t sbase = smem_u32(smem);
@@ -816,6 +824,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.n_dev == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) PHASE(1);
   const uint32_t tmem_base = *s_tmem;
   const int S = p.S, W = p.W, G = p.G;
@@ -1312,6 +1321,8 @@ __global__ void __launch_bounds__(kPlanThreads, 7) k_pair_plan(const uint32_t *_
   for (int i = tid; i * 4 < (S + 1) * (S + 2) / 2; i += kPlanThreads)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tab + 4 * i)), "l"(tabs + 4 * i) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (see k_score_tc: the graphs may come from the previous kernel of the stream)
   if (tid < S * W) s_rows[tid] = phi[(size_t)g * S * W + tid];  // 33 <= S <= 52, W = 2
   __syncthreads();
   if (closed != nullptr) {
@@ -1557,12 +1568,24 @@ int num_sms() {
   return nsm;
 }
 
+// launches of the current launch_score_tc call carry the programmatic-dependent-launch attribute (sweep entry points on
+// a stream that is not being captured; the MCMC loop's graph capture launches plainly)
+thread_local bool t_pdl = false;
+template <typename K, typename... Args>
+int launch_ex(K kern, int grid, int threads, int smem_bytes, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = t_pdl ? 1 : 0;
+  NEMB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  return 0;
+}
 template <typename K>
 int launch_kernel(K kern, const Params &p, int grid, int threads, cudaStream_t st, int smem_bytes = Lay<false>::BYTES) {
   NEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  kern<<<grid, threads, smem_bytes, st>>>(p);
-  NEMB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_ex(kern, grid, threads, smem_bytes, st, p);
 }
 
 // the specialised one-site table kernel for the dataset's column stride
@@ -1617,7 +1640,8 @@ size_t score_tc_workspace_bytes(const nemb200_dataset *h, int n, bool with_pair)
 bool score_tc_has_mix(const nemb200_dataset *h) { return h->lut_valid && h->CS == 50 && h->S == 50; }
 
 int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double *scores, void *ws, size_t ws_bytes,
-                    int impl, cudaStream_t st, int leave_sms_free, int close) {
+                    int impl, cudaStream_t st, int leave_sms_free, int close, int pdl) {
+  struct PdlScope { bool old; explicit PdlScope(bool v) : old(t_pdl) { t_pdl = v; } ~PdlScope() { t_pdl = old; } } pdl_scope(pdl != 0);
   NEMB_REQUIRE(h->S >= 8 && h->S <= 128, "tensor-core score needs 8 <= S <= 128 (S=%d)", h->S);
   // AUTO never picks the pair-merged kernel: its score kernel is faster (76 vs 103 us at S=50, E=10k, 1024 graphs)
   // but the per-graph planner costs what it saves (about 20 us per 1024 graphs); callers opt in with TC_PAIR
@@ -1704,9 +1728,11 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
     if (!(p.debug & 128) || !planned_once) {
       planned_once = true;
       if (!fused) NEMB_CHECK_CUDA(cudaMemsetAsync(fcount, 0, sizeof(int), st));
-      k_pair_plan<<<n, kPlanThreads, 0, st>>>(phi, n, h->S, h->W, h->tabs, plan, reinterpret_cast<float *>(wb + wl.tables), fslot, flist, fcount,
-                                           (p.debug & 64) ? reinterpret_cast<long long *>(wb + wl.trace) : nullptr,
-                                           close ? reinterpret_cast<uint32_t *>(wb + wl.closed) : nullptr);
+      const uint32_t *phi_c = phi; const float *tabs_c = h->tabs;
+      long long *trace_p = (p.debug & 64) ? reinterpret_cast<long long *>(wb + wl.trace) : nullptr;
+      uint32_t *closed_p = close ? reinterpret_cast<uint32_t *>(wb + wl.closed) : nullptr;
+      if (launch_ex(k_pair_plan, n, kPlanThreads, 0, st, phi_c, n, h->S, h->W, tabs_c, plan, reinterpret_cast<float *>(wb + wl.tables), fslot, flist,
+                    fcount, trace_p, closed_p)) return -1;
       NEMB_CHECK_CUDA(cudaGetLastError());
     }
     p.close = 0;  // (the planner closed the batch; the pair kernel reads the plan, the list-mode launch the closed rows)

@@ -293,10 +293,10 @@ def test_score_full_size_c3_lut_vs_witness(nb):
     for impl in TC_IMPLS + ["pair", "lut_mix"]:
         got = ds.score_bits(bits, impl=impl).cpu().numpy()
         assert np.allclose(got, w, rtol=REL_TC), impl
-    # the sweep entry's AUTO is the pair-merged path at this shape; the MCMC loop's AUTO stays with the one-site table kernel
+    # the sweep entry's AUTO is the pair-merged path at this shape, the MCMC loop's AUTO the one-site kernel with the ex2 mix
     assert np.array_equal(ds.score_bits(bits).cpu().numpy(), ds.score_bits(bits, impl="pair").cpu().numpy())
     st = ds.run_chains(orders[:128], 3, 0.01, seed=5, impl="auto")
-    assert np.array_equal(st.curr_scores.cpu().numpy(), ds.score_bits(st.curr_bits, impl="lut").cpu().numpy())
+    assert np.array_equal(st.curr_scores.cpu().numpy(), ds.score_bits(st.curr_bits, impl="lut_mix").cpu().numpy())
     perm = torch.from_numpy(rng.permutation(n)).to(bits.device)
     got_p = ds.score_bits(bits[perm].contiguous()).cpu().numpy()
     assert np.array_equal(got_p, ds.score_bits(bits).cpu().numpy()[perm.cpu().numpy()])  # deterministic
