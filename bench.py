@@ -464,8 +464,9 @@ def run_gpu(args, rank, world, local_rank):
         # is the pair-merged path: k_pair_plan (closes every graph by warp Warshall, pairs its sites, builds the pair
         # tables) -> pair-merged k_score_tc -> list-mode one-site k_score_tc for graphs the planner gave up on (none here);
         # finalize fused into the last CTA of each score launch.  Other shapes: ONE launch, closure in the expander warps.
+        # (NEMB200_SCORE_INPUTS_READY: the input batches are static, nothing on this stream writes them)
         nb._lib.check(L.nemb200_closure_score_batch(ds._h, C.c_void_p(bits.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
-                                                    C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
+                                                    C.c_void_p(ws.data_ptr()), ws.numel(), nb.engine.SCORE_INPUTS_READY, sp))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -504,7 +505,7 @@ def run_gpu(args, rank, world, local_rank):
 
     def score_only(k):
         nb._lib.check(L.nemb200_score_batch(ds._h, C.c_void_p(closed.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
-                                            C.c_void_p(ws.data_ptr()), ws.numel(), 0, sp))
+                                            C.c_void_p(ws.data_ptr()), ws.numel(), nb.engine.SCORE_INPUTS_READY, sp))
     blocks_kernel = sorted(timed(score_only, K) / K for r in range(REPEATS))
     ms_kernel = blocks_kernel[REPEATS // 2]
     # the other score implementations on the same closed batch, for comparison (not part of `value`)
@@ -514,7 +515,7 @@ def run_gpu(args, rank, world, local_rank):
             continue
         def score_impl(k, code=nb.engine.SCORE_IMPLS[name]):
             nb._lib.check(L.nemb200_score_batch(ds._h, C.c_void_p(closed.data_ptr()), CHAINS, C.c_void_p(scores.data_ptr()),
-                                                C.c_void_p(ws.data_ptr()), ws.numel(), code, sp))
+                                                C.c_void_p(ws.data_ptr()), ws.numel(), code | nb.engine.SCORE_INPUTS_READY, sp))
         with torch.cuda.stream(stream):
             for k in range(3):
                 score_impl(k)

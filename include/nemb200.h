@@ -60,6 +60,14 @@ enum {
                                   Column stride 50 (S = 50) only; AUTO of nemb200_mcmc_run's kernel loop at that stride. */
 };
 
+/* flag, OR-ed into `impl` of nemb200_score_batch / nemb200_closure_score_batch: the caller promises that the input graphs
+ * are NOT written by the kernel that precedes this call on `stream` (they are static, or they were produced earlier, or
+ * they arrive from another stream and are joined by an event).  The launches of a call are dependent launches
+ * (cudaLaunchAttributeProgrammaticStreamSerialization, never under stream capture); with the promise the first kernel
+ * reads its graphs and works ahead while the previous kernel of the stream drains, and waits for it (griddepcontrol.wait)
+ * only in front of its first write.  Without the flag it waits before its first read, as a plain launch would. */
+enum { NEMB200_SCORE_INPUTS_READY = 0x100 };
+
 typedef struct nemb200_dataset nemb200_dataset; /* opaque host handle */
 
 int nemb200_version(void);

@@ -323,17 +323,22 @@ extern "C" int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_p
                                    void *d_workspace, size_t workspace_bytes, int impl, void *stream) {
   NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
   NEMB_REQUIRE(n_graphs == 0 || (d_phi_bits && d_scores && d_workspace), "null device pointer");
-  impl = sweep_auto(h, impl);
-  return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, pdl_ok((cudaStream_t)stream));
+  const int ready = (impl & NEMB200_SCORE_INPUTS_READY) ? 1 : 0;
+  impl = sweep_auto(h, impl & ~NEMB200_SCORE_INPUTS_READY);
+  return score_dispatch(h, d_phi_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0,
+                        pdl_ok((cudaStream_t)stream) * (1 + ready));
 }
 
 extern "C" int nemb200_closure_score_batch(const nemb200_dataset *h, const uint32_t *d_adj_bits, int n_graphs, double *d_scores,
                                            void *d_workspace, size_t workspace_bytes, int impl, void *stream) {
   NEMB_REQUIRE(h != nullptr && n_graphs >= 0, "bad handle / n_graphs");
   NEMB_REQUIRE(n_graphs == 0 || (d_adj_bits && d_scores && d_workspace), "null device pointer");
+  const int ready = (impl & NEMB200_SCORE_INPUTS_READY) ? 1 : 0;
+  impl &= ~NEMB200_SCORE_INPUTS_READY;
   NEMB_REQUIRE(impl != NEMB200_SCORE_WITNESS && h->S >= 8, "closure fused into the score needs a tensor-core score kernel (S >= 8)");
   impl = sweep_auto(h, impl);
-  return launch_score_tc(h, d_adj_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, 1, pdl_ok((cudaStream_t)stream));
+  return launch_score_tc(h, d_adj_bits, n_graphs, d_scores, d_workspace, workspace_bytes, impl, (cudaStream_t)stream, 0, 1,
+                         pdl_ok((cudaStream_t)stream) * (1 + ready));
 }
 
 extern "C" int nemb200_closure_u32(const uint32_t *d_adj_bits, int n_graphs, int S, uint32_t *d_out_bits, void *stream) {

@@ -16,6 +16,7 @@ import torch
 from . import _lib
 
 RULE_FULL, RULE_MASKED, RULE_FIT = 0, 1, 2  # FIT: nemb200_mcmc_run only (the reference's per-order edge-weight fit)
+SCORE_INPUTS_READY = 0x100  # nemb200.h: flag OR-ed into impl (the graphs are not written by the stream's previous kernel)
 SCORE_IMPLS = {"auto": 0, "witness": 1, "lut": 2, "ex2": 3, "ex2_2pass": 4, "fused": 5, "pair": 6, "lutm": 7, "lut_mix": 8}
 
 
@@ -219,10 +220,12 @@ class Dataset:
 
     def max_graphs_per_launch(self) -> int:
         """Largest batch one score launch takes: the kernel's flat tile index is 32-bit (tiles x CTAs < 4e9; the
-        library refuses larger launches), so very large batches at large E are split here."""
+        library refuses larger launches), so very large batches at large E are split here.  Where AUTO is the pair-merged
+        path (9.7 KB of plan + tables per graph in the workspace) a launch takes at most 65 536 graphs."""
         per_tile = 2                                   # fewest graphs per MMA N tile of any score kernel
         n_tiles = int(3.0e9 // (self.n_mtiles * 160))  # 160 > the SM count
-        return max(per_tile * n_tiles // 1024 * 1024, 1024)
+        cap = max(per_tile * n_tiles // 1024 * 1024, 1024)
+        return min(cap, 65536) if (self.pair_ok and 44 <= self.S <= 50) else cap
 
     def _fusable(self, code) -> bool:
         """closure fused into the score (nemb200_closure_score_batch): every tensor-core kernel (the pair-merged path closes
@@ -230,11 +233,12 @@ class Dataset:
         return self.S >= 8 and code != SCORE_IMPLS["witness"]
 
     def score_bits(self, bits: torch.Tensor, impl="auto", out: torch.Tensor | None = None, stream=None,
-                   close: bool = False) -> torch.Tensor:
+                   close: bool = False, inputs_ready: bool = False) -> torch.Tensor:
         """Score bit-packed graphs already on the device; returns a float64 CUDA tensor (no sync).
         close=True: the graphs are not transitively closed yet; the score kernel closes them while it expands its
-        operand (one launch, `bits` is left untouched) - or, for the witness / pair-merged kernels and S < 8, a
-        closed copy is made first."""
+        operand, or the pair planner does (`bits` is left untouched) - or, for the witness kernel and S < 8, a
+        closed copy is made first.  inputs_ready=True: `bits` is not written by the kernel that precedes this call on
+        the stream (NEMB200_SCORE_INPUTS_READY: the call may then work ahead while that kernel drains)."""
         n = int(bits.shape[0])
         if out is None:
             out = torch.empty(n, dtype=torch.float64, device=self.device)
@@ -247,12 +251,13 @@ class Dataset:
         if close and not fused and n:
             closed = torch.empty_like(bits)
             _lib.check(L.nemb200_closure_u32(_ptr(bits), n, self.S, _ptr(closed), _stream_ptr(st)))
-            bits = closed
+            bits, inputs_ready = closed, False         # (the closure kernel just wrote them)
         fn = L.nemb200_closure_score_batch if fused else L.nemb200_score_batch
+        flag = SCORE_INPUTS_READY if inputs_ready else 0
         for lo in range(0, max(n, 1), step):           # one launch unless the batch exceeds the launch limit
             m = min(step, n - lo)
             _lib.check(fn(self._h, _ptr(bits[lo:lo + m]) if n else _ptr(bits), m, _ptr(out[lo:lo + m]) if n else _ptr(out),
-                          _ptr(ws), ws.numel(), code, _stream_ptr(st)))
+                          _ptr(ws), ws.numel(), code | flag, _stream_ptr(st)))
         return out
 
     def score_graphs(self, graphs, impl="auto", close: bool = False) -> np.ndarray:
@@ -304,8 +309,9 @@ class Dataset:
                     P["comp"].wait_event(P["drained"][b])   # the scores of batch k-2 have left this buffer
                 bits = P["bits"][b]
                 fn = L.nemb200_closure_score_batch if fused else L.nemb200_score_batch   # fused: closure inside the score kernel
-                _lib.check(fn(self._h, _ptr(bits), n, _ptr(P["scores"][b]), _ptr(P["ws"]), P["ws"].numel(), code,
-                              _stream_ptr(P["comp"])))
+                # (the graphs come from the copy stream, joined by the event above - never from the previous kernel of this stream)
+                _lib.check(fn(self._h, _ptr(bits), n, _ptr(P["scores"][b]), _ptr(P["ws"]), P["ws"].numel(),
+                              code | (SCORE_INPUTS_READY if fused or not close else 0), _stream_ptr(P["comp"])))
                 P["free"][b].record(P["comp"])
             with torch.cuda.stream(P["back"]):               # scores go back on their own stream, off the kernels' path
                 P["back"].wait_event(P["free"][b])

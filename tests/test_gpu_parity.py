@@ -190,6 +190,33 @@ def test_score_mix_only_at_stride_50(nb):
         ds.score_bits(bits, impl="lut_mix")
 
 
+@pytest.mark.parametrize("S,E,n", [(50, 3000, 600), (30, 2000, 512), (47, 1500, 300), (100, 900, 64)])
+def test_dependent_launch_back_to_back_calls(nb, S, E, n):
+    """The launches of a score call are dependent launches, and with NEMB200_SCORE_INPUTS_READY (score_bits(inputs_ready=True))
+    a call works ahead while the previous call's last kernel drains: forty calls back to back on one workspace, alternating
+    between three different batches (closed and unclosed), no synchronisation in between - every result must equal the
+    result of the same call made alone."""
+    _, _, D = orc.synth_dataset(S, E, seed=S)
+    ds = nb.Dataset(D, *orc.nem_constants(0.05, 0.1))
+    rng = np.random.default_rng(S)
+    batches = []
+    for b in range(3):
+        raw = np.stack([orc.order_to_graph(rng.permutation(S), 1, rng.random((S, S)) < 0.2, False) for _ in range(n)]).astype(np.uint8)
+        if b == 2:
+            raw[::7] = (rng.random((len(raw[::7]), S, S)) < 0.2).astype(np.uint8)   # digraphs the pair planner gives up on
+        batches.append(torch.from_numpy(nb.pack_adj(raw).view(np.int32)).cuda())
+    alone = [ds.score_bits(b, close=True).clone() for b in batches]
+    torch.cuda.synchronize()
+    outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(40)]
+    for k in range(40):
+        ds.score_bits(batches[k % 3], close=True, out=outs[k], inputs_ready=True)
+    torch.cuda.synchronize()
+    for k in range(40):
+        assert torch.equal(outs[k], alone[k % 3]), k
+    w = ds.score_bits(nb.closure(batches[2], S=S, return_bits=True), impl="witness")
+    assert torch.allclose(alone[2], w, rtol=REL_TC, atol=0)
+
+
 def test_score_other_error_rates_and_unsupported(nb):
     S, E = 40, 300
     rng = np.random.default_rng(9)
