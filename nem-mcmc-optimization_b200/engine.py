@@ -268,20 +268,24 @@ class Dataset:
         bits = _bits_to_device(graphs, self.S, self.device)
         return self.score_bits(bits, impl, close=close).cpu().numpy()
 
-    def score_stream(self, host_batches, host_out, close: bool = True, impl="auto"):
+    def score_stream(self, host_batches, host_out, close: bool = True, impl="auto", group: int = 8):
         """Score a sequence of equally-sized batches of bit-packed graphs that live in PINNED host memory
         (`host_batches[k]`: int32 tensor (n,S,W)), writing float64 scores into the pinned `host_out[k]` (n,).
-        The host->device copy of batch k+1 runs on a copy stream while batch k is closed and scored, and the
-        scores go back asynchronously: two device buffers, no host synchronisation inside (the caller
-        synchronises once at the end).  This is the end-to-end form of closure + score_batch."""
+        Batches travel in groups of `group`: the host->device copies of group g+1 run on a copy stream while group g is
+        closed and scored, and the scores of group g-1 go back on a third stream - two sets of device buffers, no host
+        synchronisation inside (the caller synchronises once at the end).  Inside a group the score calls follow each
+        other on the compute stream with nothing in between, so each call's planner works while the previous call's
+        score kernel drains (dependent launches, NEMB200_SCORE_INPUTS_READY: the graphs come from the copy stream, joined by
+        one event per group).  This is the end-to-end form of closure + score_batch."""
         if not len(host_batches):
             return
         dev = self.device
         n = int(host_batches[0].shape[0])
-        if getattr(self, "_pipe", None) is None or self._pipe["n"] != n:
-            self._pipe = {"n": n, "copy": torch.cuda.Stream(dev), "comp": torch.cuda.Stream(dev), "back": torch.cuda.Stream(dev),
-                          "bits": [torch.empty((n, self.S, self.W), dtype=torch.int32, device=dev) for _ in range(2)],
-                          "scores": [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2)],
+        group = max(1, int(group))
+        if getattr(self, "_pipe", None) is None or self._pipe["n"] != n or self._pipe["group"] != group:
+            self._pipe = {"n": n, "group": group, "copy": torch.cuda.Stream(dev), "comp": torch.cuda.Stream(dev), "back": torch.cuda.Stream(dev),
+                          "bits": [torch.empty((group, n, self.S, self.W), dtype=torch.int32, device=dev) for _ in range(2)],
+                          "scores": [torch.empty((group, n), dtype=torch.float64, device=dev) for _ in range(2)],
                           "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
                           "drained": [torch.cuda.Event() for _ in range(2)],
                           "ws": torch.empty(max(_lib.lib().nemb200_score_workspace_bytes_impl(self._h, n, SCORE_IMPLS["pair"]), 1),
@@ -294,28 +298,30 @@ class Dataset:
         P["back"].wait_stream(cur)
         code = SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl)
         fused = close and self._fusable(code)
-        for k, hb in enumerate(host_batches):
-            b = k & 1
+        fn = L.nemb200_closure_score_batch if fused else L.nemb200_score_batch   # fused: closure inside the score call
+        for gi, lo in enumerate(range(0, len(host_batches), group)):
+            b = gi & 1
+            members = list(range(lo, min(lo + group, len(host_batches))))
             with torch.cuda.stream(P["copy"]):
-                if k >= 2:
-                    P["copy"].wait_event(P["free"][b])      # batch k-2 no longer reads this buffer
-                P["bits"][b].copy_(hb, non_blocking=True)
-                if close and not fused:  # (witness / pair-merged kernels: a separate closure, beside the score kernel of batch k)
-                    _lib.check(L.nemb200_closure_u32(_ptr(P["bits"][b]), n, self.S, _ptr(P["bits"][b]), _stream_ptr(P["copy"])))
+                if gi >= 2:
+                    P["copy"].wait_event(P["free"][b])      # group gi-2 no longer reads these buffers
+                for j, k in enumerate(members):
+                    P["bits"][b][j].copy_(host_batches[k], non_blocking=True)
+                    if close and not fused:  # (witness kernel, S < 8: a separate closure, beside the score kernels of the previous group)
+                        _lib.check(L.nemb200_closure_u32(_ptr(P["bits"][b][j]), n, self.S, _ptr(P["bits"][b][j]), _stream_ptr(P["copy"])))
                 P["ready"][b].record(P["copy"])
             with torch.cuda.stream(P["comp"]):
                 P["comp"].wait_event(P["ready"][b])
-                if k >= 2:
-                    P["comp"].wait_event(P["drained"][b])   # the scores of batch k-2 have left this buffer
-                bits = P["bits"][b]
-                fn = L.nemb200_closure_score_batch if fused else L.nemb200_score_batch   # fused: closure inside the score kernel
-                # (the graphs come from the copy stream, joined by the event above - never from the previous kernel of this stream)
-                _lib.check(fn(self._h, _ptr(bits), n, _ptr(P["scores"][b]), _ptr(P["ws"]), P["ws"].numel(),
-                              code | (SCORE_INPUTS_READY if fused or not close else 0), _stream_ptr(P["comp"])))
+                if gi >= 2:
+                    P["comp"].wait_event(P["drained"][b])   # the scores of group gi-2 have left these buffers
+                for j, k in enumerate(members):
+                    _lib.check(fn(self._h, _ptr(P["bits"][b][j]), n, _ptr(P["scores"][b][j]), _ptr(P["ws"]), P["ws"].numel(),
+                                  code | SCORE_INPUTS_READY, _stream_ptr(P["comp"])))
                 P["free"][b].record(P["comp"])
             with torch.cuda.stream(P["back"]):               # scores go back on their own stream, off the kernels' path
                 P["back"].wait_event(P["free"][b])
-                host_out[k].copy_(P["scores"][b], non_blocking=True)
+                for j, k in enumerate(members):
+                    host_out[k].copy_(P["scores"][b][j], non_blocking=True)
                 P["drained"][b].record(P["back"])
         cur.wait_stream(P["comp"])
         cur.wait_stream(P["back"])

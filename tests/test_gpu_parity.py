@@ -1051,20 +1051,21 @@ def test_mcmc_fit_rule_device_loop_vs_oracle(nb, S, E, use_nem):
     assert torch.equal(st2.orders, st.orders) and torch.equal(st2.accept, st.accept)
 
 
-def test_score_stream_pipelined_host_batches(nb):
-    """Dataset.score_stream (double-buffered host->device copies against closure + score) returns, batch for
-    batch, exactly what the synchronous API returns."""
-    S, E, n = 20, 900, 96
+@pytest.mark.parametrize("S,E,n,n_batches,group", [(20, 900, 96, 5, 4), (50, 2000, 300, 11, 4), (50, 2000, 300, 7, 1), (47, 1500, 128, 9, 3)])
+def test_score_stream_pipelined_host_batches(nb, S, E, n, n_batches, group):
+    """Dataset.score_stream (groups of host->device copies double-buffered against closure + score, the calls of a group
+    chained by dependent launches) returns, batch for batch, exactly what the synchronous API returns."""
     _, _, D = orc.synth_dataset(S, E, seed=3)
     A, B = orc.nem_constants(0.05, 0.1)
     ds = nb.Dataset(D, A, B)
     rng = np.random.default_rng(0)
-    batches = [rand_dags(rng, n, S, p=0.2, closed=False) for _ in range(5)]
+    batches = [rand_dags(rng, n, S, p=0.2, closed=False) for _ in range(n_batches)]
+    batches[1][::5] = (rng.random((len(batches[1][::5]), S, S)) < 0.2).astype(np.uint8)   # digraphs (list-mode graphs at S >= 44)
     host = [torch.from_numpy(nb.pack_adj(b).view(np.int32)).pin_memory() for b in batches]
-    out = torch.zeros((5, n), dtype=torch.float64).pin_memory()
-    ds.score_stream(host, out)
+    out = torch.zeros((n_batches, n), dtype=torch.float64).pin_memory()
+    ds.score_stream(host, out, group=group)
     torch.cuda.synchronize()
-    for k in range(5):
+    for k in range(n_batches):
         assert np.array_equal(out[k].numpy(), ds.score_graphs(batches[k], close=True)), k
     ds.score_stream([], out)  # empty sequence is a no-op
 
