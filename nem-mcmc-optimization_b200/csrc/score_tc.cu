@@ -67,8 +67,8 @@ struct Lay {
   static constexpr int B = LUT + LUT_BYTES;                       // 2 buffers x (256 x 128 B)
   static constexpr int A = B + 2 * 2 * kTileBytes;                // STAGES x 16 KB
   static constexpr int BIAS = A + STAGES * kTileBytes;            // 2 buffers x 1024 floats (ex2 epilogues)
-  // (multi-level table kernel: the same region holds the level sums two warpgroups exchange, [slot 2][pair 2][3][128] floats)
-  static constexpr int ROWS = BIAS + (PAIR ? 0 : (LUT3 ? 2 * 2 * 3 * 128 * 4 : 2 * 1024 * 4));   // 1024 words of bit rows (+ 512 words of scan scratch)
+  // (multi-level table kernel: the same region holds the level sums two warpgroups exchange, [slot 2][pair 2][level 3][half 2][128] floats)
+  static constexpr int ROWS = BIAS + (PAIR ? 0 : (LUT3 ? 2 * 2 * 3 * 2 * 128 * 4 : 2 * 1024 * 4));   // 1024 words of bit rows (+ 512 words of scan scratch)
   static constexpr int RED = ROWS + 1024 * 4 + (PAIR ? 2048 : 0); // 20 warps x 8 doubles
   static constexpr int BAR = RED + 20 * 8 * 8;                    // barriers + scalars
   static constexpr int TAB = BAR + 256;                           // PAIR: 2 buffers of pair tables
@@ -399,13 +399,24 @@ __device__ __forceinline__ void level_sums_mask(uint32_t taddr, int n, float &a0
   }
 }
 // `first` (warp-uniform, from the dataset's per-E-tile range analysis): levels above it cannot be needed for this
-// tile and are not looked up - with sorted E-genes most tiles need the last level only (one look-up per site)
+// tile and are not looked up - with sorted E-genes most tiles need the last level only (one look-up per site).
+// Where the analysis allows a higher level, it is still looked up LAZILY: the last level first, and the next higher one
+// only if some E-gene of the warp has a sum of 2^119 or more there - below that, the higher level's sum (2^210 times
+// smaller, term by term) is under 2^-91 and the selection rule of levels_log (first level, from the highest scale down,
+// whose sum reaches 2^-90) rejects it anyway, so the result is bit-identical to looking everything up.  At config 4
+// (S=100, E=100 000) 36 % of the tiles allow level 0, ~40 % of those (per graph) really need it: 1.36 -> 1.15 look-ups
+// per site.
+constexpr float kLevelHi = 6.646139978924579e35f;  // 2^119 = 2^(step - T - 1), dataset.cu: step = 210, T = 90
 template <int NLEV>
-__device__ __forceinline__ void level_sums(uint32_t taddr, int n, int first, float &a0, float &a1, float &a2) {
+__device__ __forceinline__ void level_sums(uint32_t taddr, int n, int first, float &a0, float &a1, float &a2, const Params &p) {
   a0 = 0.f; a1 = 0.f; a2 = 0.f;
-  if (first >= NLEV - 1) level_sums_mask<1 << (NLEV - 1)>(taddr, n, a0, a1, a2);
-  else if (NLEV == 3 && first == 1) level_sums_mask<6>(taddr, n, a0, a1, a2);
-  else level_sums_mask<(1 << NLEV) - 1>(taddr, n, a0, a1, a2);
+  level_sums_mask<1 << (NLEV - 1)>(taddr, n, a0, a1, a2);
+  if (first >= NLEV - 1) return;
+  const float last = (NLEV == 2 ? a1 : a2) + ex2f(-p.lvl_scale[NLEV - 1]);
+  if (!__any_sync(0xffffffffu, !(last < kLevelHi))) return;
+  level_sums_mask<1 << (NLEV - 2)>(taddr, n, a0, a1, a2);
+  if (NLEV == 3 && first == 0 && __any_sync(0xffffffffu, !(a1 + ex2f(-p.lvl_scale[1]) < kLevelHi)))
+    level_sums_mask<1>(taddr, n, a0, a1, a2);
 }
 template <int NLEV>
 __device__ __forceinline__ float levels_log(float a0, float a1, float a2, const Params &p) {
@@ -420,25 +431,49 @@ __device__ __forceinline__ float levels_log(float a0, float a1, float a2, const 
 template <int NLEV>
 __device__ __forceinline__ float graph_lse_levels(uint32_t taddr, int n_cols, int first, const Params &p) {
   float a0, a1, a2;
-  level_sums<NLEV>(taddr, n_cols, first, a0, a1, a2);
+  level_sums<NLEV>(taddr, n_cols, first, a0, a1, a2, p);
   return levels_log<NLEV>(a0, a1, a2, p);
 }
 // Two graphs per tile (S > 64) would leave two of the four epilogue warpgroups idle: instead warpgroups 2h and 2h+1
-// share graph h, each sums the table entries of one half of its sites, and the odd one hands its level sums to
-// the even one through shared memory (slot = tile parity; a 256-thread named barrier per tile).  The accumulator
-// hand-back (t_empty counts all 16 warps) keeps the odd warpgroup from running two tiles ahead, so two slots suffice.
+// share graph h, each sums the table entries of one half of its sites, and they hand each other their level sums through
+// shared memory (block = tile parity; a 256-thread named barrier per tile for the last level, which every tile looks up).
+// The accumulator hand-back (t_empty counts all 16 warps) keeps a warpgroup from running two tiles ahead, so two blocks
+// suffice.  A higher level (see level_sums) is looked up by a PAIR OF WARPS - warp w of both warpgroups holds the same 32
+// E-genes and reaches the same decision from the same total - which then meet on an mbarrier of their own (64 arrivals;
+// named barriers are scarce: the MCMC accept kernel must stay co-resident).  xch: [level 3][half 2][128] floats.
 template <int NLEV>
 __device__ __forceinline__ void tile_epilogue_split(uint32_t taddr_graph, const Params &p, bool valid, int first, int half, int pair,
-                                                    float *xch, int tw, double &part0) {
+                                                    float *xch, int tw, uint32_t bar_x, uint32_t &ph_x, double &part0) {
   const int Sh = ((p.CS + 15) >> 4) << 3;  // both halves are multiples of 8 columns
-  float a0, a1, a2;
-  level_sums<NLEV>(taddr_graph + (half ? Sh : 0), half ? p.CS - Sh : Sh, first, a0, a1, a2);
-  if (half) { xch[tw] = a0; xch[128 + tw] = a1; if (NLEV > 2) xch[256 + tw] = a2; }
-  if (pair == 0) asm volatile("bar.sync 8, 256;" ::: "memory"); else asm volatile("bar.sync 9, 256;" ::: "memory");
+  const uint32_t ta = taddr_graph + (half ? Sh : 0);
+  const int nc = half ? p.CS - Sh : Sh;
+  float tot[3] = {0.f, 0.f, 0.f};
+  // one level: my half's sum, the partner's through shared memory, total = even half + odd half (the same bits in both)
+  auto level = [&](auto lv_c, bool first_exchange) {
+    constexpr int LV = decltype(lv_c)::value;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    level_sums_mask<1 << LV>(ta, nc, m0, m1, m2);
+    const float mine = LV == 0 ? m0 : (LV == 1 ? m1 : m2);
+    xch[(LV * 2 + half) * 128 + tw] = mine;
+    if (first_exchange) {
+      if (pair == 0) asm volatile("bar.sync 8, 256;" ::: "memory"); else asm volatile("bar.sync 9, 256;" ::: "memory");
+    } else {
+      mbar_arrive(bar_x);
+      mbar_wait(bar_x, ph_x);
+      ph_x ^= 1u;
+    }
+    const float other = xch[(LV * 2 + (half ^ 1)) * 128 + tw];
+    tot[LV] = half ? other + mine : mine + other;
+  };
+  level(std::integral_constant<int, NLEV - 1>{}, true);
+  if (first < NLEV - 1 && __any_sync(0xffffffffu, !(tot[NLEV - 1] + ex2f(-p.lvl_scale[NLEV - 1]) < kLevelHi))) {
+    level(std::integral_constant<int, NLEV - 2>{}, false);
+    if constexpr (NLEV == 3) {
+      if (first == 0 && __any_sync(0xffffffffu, !(tot[1] + ex2f(-p.lvl_scale[1]) < kLevelHi))) level(std::integral_constant<int, 0>{}, false);
+    }
+  }
   if (!half) {
-    a0 += xch[tw]; a1 += xch[128 + tw];
-    if (NLEV > 2) a2 += xch[256 + tw];
-    const float l = levels_log<NLEV>(a0, a1, a2, p);
+    const float l = levels_log<NLEV>(tot[0], tot[1], tot[2], p);
     if (valid) part0 += (double)l;
   }
 }
@@ -792,6 +827,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
   // barrier map: a_full[4] a_empty[4] t_full[2] t_empty[2] b_full[2] e_done[2]
   const uint32_t bar_afull = sbase + L::BAR, bar_aempty = bar_afull + 8 * 4, bar_tfull = bar_aempty + 8 * 4,
                  bar_tempty = bar_tfull + 16, bar_bfull = bar_tempty + 16, bar_edone = bar_bfull + 16;
+  [[maybe_unused]] const uint32_t bar_xch = bar_afull + 160;  // EPI_LUTM, split epilogue: [pair 2][warp 4] mbarriers of 64 arrivals (after the 16 above + s_tmem)
   volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(bars + 2 * 4 + 8);
   uint32_t *sRows = reinterpret_cast<uint32_t *>(smem + L::ROWS);
   double *sRed = reinterpret_cast<double *>(smem + L::RED);
@@ -801,6 +837,9 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4 * NWG);
       mbar_init(bar_bfull + 8 * i, 2); mbar_init(bar_edone + 8 * i, 4 * NWG);
+    }
+    if constexpr (EPI == EPI_LUTM) {
+      for (int i = 0; i < 8; ++i) mbar_init(bar_xch + 8 * i, 64);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1158,6 +1197,7 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
     const int wg = (warp - 4) >> 2, quarter = warp & 3, tw = threadIdx.x - 128 - wg * 128;
     const int gq = G >= NWG ? G / NWG : 1;                       // graphs per warpgroup (G == 2: warpgroups 2,3 idle)
     const bool split = EPI == EPI_LUTM && G == 2;                // ... unless two warpgroups share a graph (tile_epilogue_split)
+    [[maybe_unused]] uint32_t ph_xch = 0;                        // phase of this warp pair's exchange mbarrier (split epilogue)
     const int bstride = kBiasStride * (S > 64 ? 2 : 1);
     uint32_t it = 0;
     Walker wk(n_ntiles, p.n_mtiles, (int)gridDim.x, (int)blockIdx.x);
@@ -1198,7 +1238,8 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
               const int first = (int)p.tile_first[m0 + t];
               if (split)
                 tile_epilogue_split<NLUT>(taddr, p, valid, first, wg & 1, wg >> 1,
-                                          reinterpret_cast<float *>(smem + L::BIAS) + ((buf * 2 + (wg >> 1)) * 3) * 128, tw, part[0]);
+                                          reinterpret_cast<float *>(smem + L::BIAS) + ((buf * 2 + (wg >> 1)) * 6) * 128, tw,
+                                          bar_xch + 8u * (uint32_t)((wg >> 1) * 4 + quarter), ph_xch, part[0]);
               else
                 tile_epilogue_generic<EPI, NLUT>(taddr, bias, p, valid, ng_mine, part, first);
             } else {
