@@ -213,6 +213,18 @@ def test_dependent_launch_back_to_back_calls(nb, S, E, n):
     torch.cuda.synchronize()
     for k in range(40):
         assert torch.equal(outs[k], alone[k % 3]), k
+    # without the promise: the graphs are produced by the kernel right before the call (an element-wise torch kernel into a
+    # buffer that is rewritten every time), promised and unpromised calls interleaved
+    buf = torch.empty_like(batches[0])
+    for k in range(24):
+        if k % 2:
+            torch.bitwise_xor(batches[k % 3], 0, out=buf)
+            ds.score_bits(buf, close=True, out=outs[k])
+        else:
+            ds.score_bits(batches[k % 3], close=True, out=outs[k], inputs_ready=True)
+    torch.cuda.synchronize()
+    for k in range(24):
+        assert torch.equal(outs[k], alone[k % 3]), k
     w = ds.score_bits(nb.closure(batches[2], S=S, return_bits=True), impl="witness")
     assert torch.allclose(alone[2], w, rtol=REL_TC, atol=0)
 
