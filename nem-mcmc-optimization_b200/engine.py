@@ -271,7 +271,7 @@ class Dataset:
     def score_stream(self, host_batches, host_out, close: bool = True, impl="auto", group: int = 8):
         """Score a sequence of equally-sized batches of bit-packed graphs that live in PINNED host memory
         (`host_batches[k]`: int32 tensor (n,S,W)), writing float64 scores into the pinned `host_out[k]` (n,).
-        Batches travel in groups of `group`: the host->device copies of group g+1 run on a copy stream while group g is
+        Batches travel in groups of up to `group` (1, 2, 4, ... at the start): the host->device copies of group g+1 run on a copy stream while group g is
         closed and scored, and the scores of group g-1 go back on a third stream - two sets of device buffers, no host
         synchronisation inside (the caller synchronises once at the end).  Inside a group the score calls follow each
         other on the compute stream with nothing in between, so each call's planner works while the previous call's
@@ -299,9 +299,14 @@ class Dataset:
         code = SCORE_IMPLS[impl] if isinstance(impl, str) else int(impl)
         fused = close and self._fusable(code)
         fn = L.nemb200_closure_score_batch if fused else L.nemb200_score_batch   # fused: closure inside the score call
-        for gi, lo in enumerate(range(0, len(host_batches), group)):
+        # group sizes ramp up 1, 2, 4, ... to `group`: the first kernels start after ONE copy, not after a whole group's
+        bounds, lo, size = [], 0, 1
+        while lo < len(host_batches):
+            bounds.append((lo, min(lo + size, len(host_batches))))
+            lo, size = lo + size, min(2 * size, group)
+        for gi, (lo, hi) in enumerate(bounds):
             b = gi & 1
-            members = list(range(lo, min(lo + group, len(host_batches))))
+            members = list(range(lo, hi))
             with torch.cuda.stream(P["copy"]):
                 if gi >= 2:
                     P["copy"].wait_event(P["free"][b])      # group gi-2 no longer reads these buffers
