@@ -15,7 +15,7 @@
 // K row adds the table's shared-memory base so the accumulator IS the address.  Epilogue "EX2": the same
 // accumulator is mapped linearly to the log2-domain value and exponentiated with ex2.approx (any S<=128);
 // "EX2_2PASS" subtracts the running maximum first (any dynamic range).  For every S <= 63 the table epilogue is
-// compiled for a fixed column stride (straight-line, software-pipelined over tiles).  "PAIR" (opt-in): a planner
+// compiled for a fixed column stride (straight-line, software-pipelined over tiles).  "PAIR" (AUTO of the sweep entries for 44 <= S <= 50): a planner
 // merges pairs of sites so that one look-up serves two of them (k_pair_plan below).
 // No B x S x E intermediate ever reaches HBM: per (graph, CTA piece of its N tile) one double is written.
 //
@@ -1696,8 +1696,9 @@ int launch_score_tc(const nemb200_dataset *h, const uint32_t *phi, int n, double
                     int impl, cudaStream_t st, int leave_sms_free, int close, int pdl) {
   struct PdlScope { bool old; explicit PdlScope(bool v) : old(t_pdl) { t_pdl = v; } ~PdlScope() { t_pdl = old; } } pdl_scope(pdl != 0);
   NEMB_REQUIRE(h->S >= 8 && h->S <= 128, "tensor-core score needs 8 <= S <= 128 (S=%d)", h->S);
-  // AUTO never picks the pair-merged kernel: its score kernel is faster (76 vs 103 us at S=50, E=10k, 1024 graphs)
-  // but the per-graph planner costs what it saves (about 20 us per 1024 graphs); callers opt in with TC_PAIR
+  // AUTO at THIS level (what the MCMC loop reaches) is a one-site kernel: the pair-merged path would run its planner per
+  // chain group and iteration (95 vs 94 us).  The sweep entry points resolve AUTO themselves (mcmc.cu: sweep_auto) and pick
+  // the pair-merged path for 44 <= S <= 50.
   if (impl == NEMB200_SCORE_AUTO)
     impl = h->lut_valid ? NEMB200_SCORE_TC_LUT
                         : (h->fixed_valid ? NEMB200_SCORE_TC_EX2 : (h->lutm_levels > 0 ? NEMB200_SCORE_TC_LUTM : NEMB200_SCORE_TC_EX2_2PASS));
