@@ -111,7 +111,8 @@ int nemb200_transitive_reduction_u32(const uint32_t *d_adj_bits, int n_graphs, i
  *      d_workspace: nemb200_score_workspace_bytes(h, n_graphs) bytes. */
 size_t nemb200_score_workspace_bytes(const nemb200_dataset *h, int n_graphs);
 /* the same for one specific `impl`: NEMB200_SCORE_TC_PAIR needs room for its plan and pair tables
- * (about 9 KB per graph); every other implementation fits nemb200_score_workspace_bytes(). */
+ * (about 10 KB per graph); every other implementation fits nemb200_score_workspace_bytes(), which is the size for
+ * NEMB200_SCORE_AUTO (it includes the pair-merged path's room where AUTO resolves to it, 44 <= S <= 50). */
 size_t nemb200_score_workspace_bytes_impl(const nemb200_dataset *h, int n_graphs, int impl);
 int nemb200_score_batch(const nemb200_dataset *h, const uint32_t *d_phi_bits, int n_graphs,
                         double *d_scores, void *d_workspace, size_t workspace_bytes, int impl,
