@@ -1310,12 +1310,13 @@ __global__ void __launch_bounds__(cta_threads(S_T), 1) k_score_tc(const Params p
       const double sumN = *p.sumN;
       const int ctas_eff = effective_ctas(T, p.n_mtiles, (int)gridDim.x);  // (list mode launches a full grid for a list it cannot see)
       for (int g = threadIdx.x; g < n_graphs; g += cta_threads(S_T)) {
-        if (p.fbslot != nullptr && __ldcg(p.fbslot + g) >= 0) continue;  // scored by the one-site kernel (list mode)
+        const int fb = p.fbslot != nullptr ? __ldcg(p.fbslot + g) : -1;  // (in flight together with the partial sums: -0.5 us per call)
         const int cnt = slots_of_ntile(g / G, p.n_mtiles, T, ctas_eff);
         const double *src = p.partials + (size_t)g * p.n_slots;
         // (the first four slots - all there are unless E is huge - are fetched together: one L2 round trip, same order of additions)
         const double s0 = __ldcg(src), s1 = cnt > 1 ? __ldcg(src + 1) : 0.0, s2 = cnt > 2 ? __ldcg(src + 2) : 0.0,
                      s3 = cnt > 3 ? __ldcg(src + 3) : 0.0;
+        if (fb >= 0) continue;  // scored by the one-site kernel (list mode)
         double v = s0;
         if (cnt > 1) v += s1;
         if (cnt > 2) v += s2;
